@@ -1,0 +1,815 @@
+// emub_api.cu -- host orchestration + C-ABI (include/emu_b200.h) of the B200 GP engine.
+//
+// Data layout in HBM, per model (npad = n rounded up to 128, the padding is an identity block so
+// that no kernel needs edge predication; nblk = npad / 128):
+//   X   (npad x d)            design, padded rows zero
+//   Yh  (npad x ncp)          [ y | H | 0 ]  (ncp = p + 1 rounded up to 8)
+//   per slot (one in-flight likelihood evaluation):
+//     bufA (npad x npad)      C -> L (in place, lower) -> Cinv = W^T W (lower tiles)
+//     bufW (npad x npad)      W = L^-1 (lower; diagonal blocks from POTF2, the rest by recursive merge)
+//     bufT (npad x npad)      merge temporary  T = L21 W11
+//     UG (npad x ncp)         W [y | H]      AB (npad x ncp)  W^T UG = [alpha | C^-1 H]
+//     small per-slot arrays (constants, log-det partials, Gram partials, gradient partials, results)
+//
+// One likelihood + gradient evaluation (reference: evalFnGradMulti, maxmultimin.c:615) is
+//   K1 covariance (lower) -> blocked right-looking Cholesky (POTF2 on the diagonal block, DMMA
+//   TRSM-as-GEMM panel, DMMA SYRK trailing update) -> recursive triangular inverse (DMMA) ->
+//   skinny products + p x p regression algebra -> DMMA W^T W -> fused gradient reduction.
+// Slots are processed in lock step per stream group, groups run concurrently on their own streams.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/emu_b200.h"
+#include "emub_gemm.cuh"
+#include "emub_kernels.cuh"
+
+using namespace emub;
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char *fmt, const char *a = "", int line = 0)
+{
+	snprintf(g_err, sizeof(g_err), fmt, a, line);
+	return code;
+}
+#define CUDA_TRY(expr)                                                                             \
+	do {                                                                                           \
+		cudaError_t e__ = (expr);                                                                  \
+		if (e__ != cudaSuccess) return set_err(EMUB_ECUDA, "CUDA: %s (emub_api.cu:%d)", cudaGetErrorString(e__), __LINE__); \
+	} while (0)
+
+static const char *k_family_names[EMUB_K_NFAMILIES] = {"cov", "potf2", "gemm_chol", "gemm_trtri", "gemm_lauum", "skinny",
+                                                       "small", "grad", "kcross", "gemm_pred", "pred_final"};
+
+struct ProfAcc { double ms; long long launches; double work; };
+
+struct emub_ctx {
+	int device;
+	int ngroups;
+	cudaStream_t streams[4];
+	int profile;
+	ProfAcc prof[EMUB_K_NFAMILIES];
+	long long launches;
+	cudaEvent_t ev0, ev1;
+	cudaEvent_t gev[4];
+};
+
+// launch bookkeeping: in profile mode every launch is timed on its own (events + sync)
+struct LaunchScope {
+	emub_ctx *c; int fam; double work; cudaStream_t st;
+	LaunchScope(emub_ctx *c_, int fam_, double work_, cudaStream_t st_) : c(c_), fam(fam_), work(work_), st(st_)
+	{
+		c->launches++;
+		if (c->profile) cudaEventRecord(c->ev0, st);
+	}
+	~LaunchScope()
+	{
+		if (c->profile) {
+			cudaEventRecord(c->ev1, st);
+			cudaEventSynchronize(c->ev1);
+			float ms = 0.f;
+			cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+			c->prof[fam].ms += ms;
+			c->prof[fam].launches++;
+			c->prof[fam].work += work;
+		}
+	}
+};
+
+struct TrtriLevel { int t1_off, t1_cnt, t2_off, t2_cnt; double flops1, flops2; };
+
+struct emub_model {
+	emub_ctx *ctx;
+	int n, d, p, ncp, kernel, order, nth, npad, nblk, nslots;
+	size_t mat;  // npad * npad
+	double *dX, *dy, *dYh;
+	GemmTask *dTasks;
+	std::vector<int> trsm_off, trsm_cnt, syrk_off, syrk_cnt;
+	std::vector<TrtriLevel> levels;
+	int lauum_off, lauum_cnt;
+	double lauum_flops;
+	double *bufA, *bufW, *bufT;
+	double *dUG, *dAB, *dConsts, *dLogdet, *dGramPart, *dRes, *dGradPart, *dMinv, *dThetas, *dOut;
+	int *dInfo;
+	double *hThetas, *hRes;  // pinned
+	int last_count;
+};
+
+struct emub_emulator {
+	emub_model *m;
+	double *W, *AB, *beta, *Minv, *consts;
+	double kappa;
+	int mqc;  // query chunk (multiple of 128)
+	double *dQ, *dK, *dVsq, *dKA, *dMean, *dVar;
+	GemmTask *dTasks;
+	double *hQ, *hOut;  // pinned
+	double hbeta[MAXNCP];
+};
+
+extern "C" const char *emub_last_error(void) { return g_err; }
+extern "C" const char *emub_version(void) { return "emub 0.1 (sm_100a, FP64 DMMA)"; }
+extern "C" const char *emub_profile_name(int f) { return (f >= 0 && f < EMUB_K_NFAMILIES) ? k_family_names[f] : "?"; }
+
+extern "C" int emub_ctx_create(int device, emub_ctx **out)
+{
+	if (!out) return set_err(EMUB_EINVAL, "emub_ctx_create: null out%s");
+	int ndev = 0;
+	CUDA_TRY(cudaGetDeviceCount(&ndev));
+	if (device < 0 || device >= ndev) return set_err(EMUB_EINVAL, "emub_ctx_create: no such device%s");
+	CUDA_TRY(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) return set_err(EMUB_ECUDA, "emub: device is not sm_100 class (%s)", prop.name);
+	emub_ctx *c = new emub_ctx();
+	memset(c, 0, sizeof(*c));
+	c->device = device;
+	c->ngroups = 2;
+	for (int g = 0; g < 4; g++) {
+		CUDA_TRY(cudaStreamCreateWithFlags(&c->streams[g], cudaStreamNonBlocking));
+		CUDA_TRY(cudaEventCreateWithFlags(&c->gev[g], cudaEventDisableTiming));
+	}
+	CUDA_TRY(cudaEventCreate(&c->ev0));
+	CUDA_TRY(cudaEventCreate(&c->ev1));
+	// opt in to large dynamic shared memory once
+	CUDA_TRY(cudaFuncSetAttribute(k_gemm<KMAJOR, KMAJOR, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+	CUDA_TRY(cudaFuncSetAttribute(k_gemm<KMAJOR, KMAJOR, EPI_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+	CUDA_TRY(cudaFuncSetAttribute(k_gemm<KMAJOR, RMAJOR, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+	CUDA_TRY(cudaFuncSetAttribute(k_gemm<RMAJOR, RMAJOR, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+	CUDA_TRY(cudaFuncSetAttribute(k_gemm<KMAJOR, RMAJOR, EPI_COLSUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+	CUDA_TRY(cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
+	*out = c;
+	return EMUB_OK;
+}
+
+extern "C" void emub_ctx_destroy(emub_ctx *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaDeviceSynchronize();
+	for (int g = 0; g < 4; g++) { cudaStreamDestroy(c->streams[g]); cudaEventDestroy(c->gev[g]); }
+	cudaEventDestroy(c->ev0);
+	cudaEventDestroy(c->ev1);
+	delete c;
+}
+extern "C" void *emub_ctx_stream(emub_ctx *c) { return c ? (void *)c->streams[0] : nullptr; }
+extern "C" int emub_ctx_set_groups(emub_ctx *c, int ng)
+{
+	if (!c || ng < 1 || ng > 4) return set_err(EMUB_EINVAL, "emub_ctx_set_groups: 1..4%s");
+	c->ngroups = ng;
+	return EMUB_OK;
+}
+extern "C" int emub_ctx_synchronize(emub_ctx *c)
+{
+	if (!c) return EMUB_EINVAL;
+	CUDA_TRY(cudaSetDevice(c->device));
+	for (int g = 0; g < 4; g++) CUDA_TRY(cudaStreamSynchronize(c->streams[g]));
+	return EMUB_OK;
+}
+extern "C" int emub_profile_enable(emub_ctx *c, int on) { if (!c) return EMUB_EINVAL; c->profile = on ? 1 : 0; return EMUB_OK; }
+extern "C" int emub_profile_reset(emub_ctx *c) { if (!c) return EMUB_EINVAL; memset(c->prof, 0, sizeof(c->prof)); return EMUB_OK; }
+extern "C" int emub_profile_read(emub_ctx *c, int f, double *ms, long long *launches, double *work)
+{
+	if (!c || f < 0 || f >= EMUB_K_NFAMILIES) return EMUB_EINVAL;
+	if (ms) *ms = c->prof[f].ms;
+	if (launches) *launches = c->prof[f].launches;
+	if (work) *work = c->prof[f].work;
+	return EMUB_OK;
+}
+extern "C" long long emub_launch_count(emub_ctx *c) { return c ? c->launches : 0; }
+
+// ---- schedules --------------------------------------------------------------------------------------
+static void build_schedules(emub_model *m, std::vector<GemmTask> &tasks)
+{
+	const long long ld = m->npad;
+	const int nb = m->nblk;
+	auto off = [&](int bi, int bj) { return (long long)bi * TB * ld + (long long)bj * TB; };
+	m->trsm_off.assign(nb, 0); m->trsm_cnt.assign(nb, 0); m->syrk_off.assign(nb, 0); m->syrk_cnt.assign(nb, 0);
+	for (int k = 0; k < nb; k++) {
+		m->trsm_off[k] = (int)tasks.size();
+		for (int i = k + 1; i < nb; i++) tasks.push_back({off(i, k), off(k, k), off(i, k), TB, 0});
+		m->trsm_cnt[k] = (int)tasks.size() - m->trsm_off[k];
+		m->syrk_off[k] = (int)tasks.size();
+		for (int i = k + 1; i < nb; i++)
+			for (int j = k + 1; j <= i; j++) tasks.push_back({off(i, k), off(j, k), off(i, j), TB, 0});
+		m->syrk_cnt[k] = (int)tasks.size() - m->syrk_off[k];
+	}
+	// recursive triangular inverse: level sb merges [c0, c0+sb) and [c0+sb, min(c0+2sb, nb))
+	for (int sb = 1; sb < nb; sb *= 2) {
+		TrtriLevel L{};
+		std::vector<GemmTask> t1, t2;
+		for (int c0 = 0; c0 < nb; c0 += 2 * sb) {
+			const int mid = c0 + sb;
+			if (mid >= nb) continue;
+			const int c1 = std::min(c0 + 2 * sb, nb);
+			for (int i = mid; i < c1; i++)
+				for (int j = c0; j < mid; j++) {
+					// T(i,j) = sum_{k in [j, mid)} L(i,k) W(k,j)       A = L KMAJOR, B = W RMAJOR
+					t1.push_back({off(i, j), off(j, j), off(i, j), (mid - j) * TB, 0});
+					// W(i,j) = - sum_{k in [mid, i]} W(i,k) T(k,j)     A = W KMAJOR, B = T RMAJOR
+					t2.push_back({off(i, mid), off(mid, j), off(i, j), (i + 1 - mid) * TB, 0});
+				}
+		}
+		auto by_k = [](const GemmTask &a, const GemmTask &b) { return a.klen > b.klen; };
+		std::stable_sort(t1.begin(), t1.end(), by_k);
+		std::stable_sort(t2.begin(), t2.end(), by_k);
+		L.t1_off = (int)tasks.size(); L.t1_cnt = (int)t1.size();
+		for (auto &t : t1) { tasks.push_back(t); L.flops1 += 2.0 * TB * TB * t.klen; }
+		L.t2_off = (int)tasks.size(); L.t2_cnt = (int)t2.size();
+		for (auto &t : t2) { tasks.push_back(t); L.flops2 += 2.0 * TB * TB * t.klen; }
+		m->levels.push_back(L);
+	}
+	// Cinv(i,j) = sum_{k >= i} W(k,i)^T W(k,j), i >= j     A = W RMAJOR, B = W RMAJOR
+	m->lauum_off = (int)tasks.size();
+	m->lauum_flops = 0;
+	for (int i = 0; i < nb; i++)
+		for (int j = 0; j <= i; j++) {
+			tasks.push_back({off(i, i), off(i, j), off(i, j), (nb - i) * TB, 0});
+			m->lauum_flops += 2.0 * TB * TB * (double)(nb - i) * TB;
+		}
+	m->lauum_cnt = (int)tasks.size() - m->lauum_off;
+}
+
+static int regression_fns(int order, int d) { if (order < 0 || order > 3) order = 0; return 1 + order * d; }
+
+extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n, int d, const double *y, int kernel,
+                                 int order, int max_slots, emub_model **out)
+{
+	if (!ctx || !X || !y || !out) return set_err(EMUB_EINVAL, "emub_model_create: null argument%s");
+	if (n < 1 || d < 1 || d > MAXD || ldx < d) return set_err(EMUB_EINVAL, "emub_model_create: need 1 <= d <= 32, n >= 1%s");
+	if (kernel < 1 || kernel > 3) kernel = EMUB_POWEREXP;  // multi_modelstruct.c:67-74 falls back to power-exp
+	if (order < 0 || order > 3) order = 0;
+	const int p = regression_fns(order, d);
+	if (p + 1 > MAXNCP) return set_err(EMUB_EINVAL, "emub_model_create: 1 + order*d + 1 must be <= 48%s");
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	emub_model *m = new emub_model();
+	m->ctx = ctx; m->n = n; m->d = d; m->p = p; m->kernel = kernel; m->order = order;
+	m->ncp = ((p + 1) + 7) / 8 * 8;
+	m->nth = (kernel == EMUB_POWEREXP) ? d + 2 : 3;
+	m->npad = (n + TB - 1) / TB * TB;
+	m->nblk = m->npad / TB;
+	m->mat = (size_t)m->npad * m->npad;
+	m->last_count = 0;
+	size_t free_b = 0, total_b = 0;
+	CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+	const size_t per_slot = 3 * m->mat * sizeof(double) + (size_t)m->npad * m->ncp * 16 + (1 << 20);
+	int slots = (int)std::min<size_t>(64, (size_t)(0.6 * (double)free_b) / per_slot);
+	if (max_slots > 0) slots = std::min(slots, max_slots);
+	if (slots < 1) { delete m; return set_err(EMUB_ENOMEM, "emub_model_create: not enough device memory for one slot%s"); }
+	m->nslots = slots;
+
+	std::vector<double> Xp((size_t)m->npad * d, 0.0);
+	for (int i = 0; i < n; i++) memcpy(&Xp[(size_t)i * d], X + (size_t)i * ldx, sizeof(double) * d);
+	CUDA_TRY(cudaMalloc(&m->dX, Xp.size() * sizeof(double)));
+	CUDA_TRY(cudaMemcpy(m->dX, Xp.data(), Xp.size() * sizeof(double), cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMalloc(&m->dy, sizeof(double) * n));
+	CUDA_TRY(cudaMemcpy(m->dy, y, sizeof(double) * n, cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMalloc(&m->dYh, sizeof(double) * (size_t)m->npad * m->ncp));
+	std::vector<GemmTask> tasks;
+	build_schedules(m, tasks);
+	if (tasks.empty()) tasks.push_back({0, 0, 0, 0, 0});
+	CUDA_TRY(cudaMalloc(&m->dTasks, tasks.size() * sizeof(GemmTask)));
+	CUDA_TRY(cudaMemcpy(m->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
+	const size_t S = slots;
+	CUDA_TRY(cudaMalloc(&m->bufA, S * m->mat * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->bufW, S * m->mat * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->bufT, S * m->mat * sizeof(double)));
+	CUDA_TRY(cudaMemset(m->bufW, 0, S * m->mat * sizeof(double)));
+	CUDA_TRY(cudaMemset(m->bufT, 0, S * m->mat * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->dUG, S * m->npad * m->ncp * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->dAB, S * m->npad * m->ncp * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->dConsts, S * CONST_STRIDE * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->dLogdet, S * m->nblk * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->dGramPart, S * m->nblk * MAXNCP * MAXNCP * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->dRes, S * RES_STRIDE * sizeof(double)));
+	const size_t nt64 = m->npad / CT, ntl = nt64 * (nt64 + 1) / 2;
+	CUDA_TRY(cudaMalloc(&m->dGradPart, S * ntl * MAXD * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->dMinv, S * MAXNCP * MAXNCP * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->dThetas, S * (MAXD + 2) * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->dOut, S * (MAXD + 6) * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&m->dInfo, S * sizeof(int)));
+	CUDA_TRY(cudaMallocHost(&m->hThetas, S * (MAXD + 2) * sizeof(double)));
+	CUDA_TRY(cudaMallocHost(&m->hRes, S * RES_STRIDE * sizeof(double)));
+	cudaStream_t st = ctx->streams[0];
+	{
+		LaunchScope ls(ctx, EMUB_K_SMALL, 0, st);
+		k_build_yh<<<(m->npad + 127) / 128, 128, 0, st>>>(m->dX, m->dy, n, m->npad, d, order, m->ncp, m->dYh);
+	}
+	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(cudaGetLastError());
+	*out = m;
+	return EMUB_OK;
+}
+
+extern "C" void emub_model_destroy(emub_model *m)
+{
+	if (!m) return;
+	cudaSetDevice(m->ctx->device);
+	cudaDeviceSynchronize();
+	cudaFree(m->dX); cudaFree(m->dy); cudaFree(m->dYh); cudaFree(m->dTasks);
+	cudaFree(m->bufA); cudaFree(m->bufW); cudaFree(m->bufT);
+	cudaFree(m->dUG); cudaFree(m->dAB); cudaFree(m->dConsts); cudaFree(m->dLogdet); cudaFree(m->dGramPart);
+	cudaFree(m->dRes); cudaFree(m->dGradPart); cudaFree(m->dMinv); cudaFree(m->dThetas); cudaFree(m->dOut); cudaFree(m->dInfo);
+	cudaFreeHost(m->hThetas); cudaFreeHost(m->hRes);
+	delete m;
+}
+extern "C" int emub_model_nthetas(const emub_model *m) { return m ? m->nth : 0; }
+extern "C" int emub_model_nregression_fns(const emub_model *m) { return m ? m->p : 0; }
+extern "C" int emub_model_slots(const emub_model *m) { return m ? m->nslots : 0; }
+
+extern "C" int emub_model_set_training(emub_model *m, const double *y)
+{
+	if (!m || !y) return set_err(EMUB_EINVAL, "emub_model_set_training: null%s");
+	CUDA_TRY(cudaSetDevice(m->ctx->device));
+	cudaStream_t st = m->ctx->streams[0];
+	CUDA_TRY(cudaMemcpyAsync(m->dy, y, sizeof(double) * m->n, cudaMemcpyHostToDevice, st));
+	{
+		LaunchScope ls(m->ctx, EMUB_K_SMALL, 0, st);
+		k_set_y<<<(m->n + 127) / 128, 128, 0, st>>>(m->dy, m->n, m->ncp, m->dYh);
+	}
+	CUDA_TRY(cudaStreamSynchronize(st));
+	return EMUB_OK;
+}
+
+// ---- kernel launch helpers ----------------------------------------------------------------------------
+template <int AL, int BL, int EPI>
+static void launch_gemm(emub_ctx *c, int fam, double flops, cudaStream_t st, const GemmTask *tasks, int ntasks, int batch,
+                        const double *A, long long sA, int lda, const double *B, long long sB, int ldb, double *C,
+                        long long sC, int ldc, double alpha)
+{
+	if (ntasks <= 0 || batch <= 0) return;
+	GemmArgs a{tasks, A, B, C, sA, sB, sC, lda, ldb, ldc, alpha};
+	LaunchScope ls(c, fam, flops * batch, st);
+	k_gemm<AL, BL, EPI><<<dim3(ntasks, batch), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(a);
+}
+
+static void launch_cov(emub_model *m, cudaStream_t st, int count, const double *consts, double *out, long long ostride,
+                       int lower_only)
+{
+	const int nt = m->npad / CT;
+	const size_t smem = 2 * (size_t)m->d * CT * sizeof(double);
+	const double bytes = (lower_only ? 0.5 : 1.0) * 8.0 * (double)m->npad * m->npad + 8.0 * m->npad * m->d;
+	LaunchScope ls(m->ctx, EMUB_K_COV, bytes * count, st);
+	dim3 grid(nt, nt, count);
+	switch (m->kernel) {
+	case 2: k_cov<2, false><<<grid, 256, smem, st>>>(m->dX, m->n, m->d, nullptr, 0, consts, CONST_STRIDE, out, ostride, m->npad, lower_only); break;
+	case 3: k_cov<3, false><<<grid, 256, smem, st>>>(m->dX, m->n, m->d, nullptr, 0, consts, CONST_STRIDE, out, ostride, m->npad, lower_only); break;
+	default: k_cov<1, false><<<grid, 256, smem, st>>>(m->dX, m->n, m->d, nullptr, 0, consts, CONST_STRIDE, out, ostride, m->npad, lower_only); break;
+	}
+}
+
+static void launch_kcross(emub_model *m, cudaStream_t st, const double *consts, const double *dQ, int mq, int mq_pad,
+                          double *dK, int ldk)
+{
+	const size_t smem = 2 * (size_t)m->d * CT * sizeof(double);
+	LaunchScope ls(m->ctx, EMUB_K_KCROSS, 8.0 * (double)m->npad * mq_pad, st);
+	dim3 grid(mq_pad / CT, m->npad / CT, 1);
+	switch (m->kernel) {
+	case 2: k_cov<2, true><<<grid, 256, smem, st>>>(m->dX, m->n, m->d, dQ, mq, consts, 0, dK, 0, ldk, 0); break;
+	case 3: k_cov<3, true><<<grid, 256, smem, st>>>(m->dX, m->n, m->d, dQ, mq, consts, 0, dK, 0, ldk, 0); break;
+	default: k_cov<1, true><<<grid, 256, smem, st>>>(m->dX, m->n, m->d, dQ, mq, consts, 0, dK, 0, ldk, 0); break;
+	}
+}
+
+// Cholesky (in place in bufA, diagonal-block inverses into bufW) for `count` slots starting at s0
+static void run_cholesky(emub_model *m, cudaStream_t st, int s0, int count)
+{
+	emub_ctx *c = m->ctx;
+	const int ld = m->npad;
+	double *A = m->bufA + (size_t)s0 * m->mat, *W = m->bufW + (size_t)s0 * m->mat;
+	for (int k = 0; k < m->nblk; k++) {
+		{
+			LaunchScope ls(c, EMUB_K_POTF2, count * (2.0 * TB * TB * TB / 3.0), st);
+			k_potf2<<<count, POTF2_THREADS, POTF2_SMEM_BYTES, st>>>(A, (long long)m->mat, W, (long long)m->mat, ld, k, m->nblk,
+			                                                        m->dLogdet + (size_t)s0 * m->nblk, m->dInfo + s0);
+		}
+		// L(i,k) = A(i,k) Winv(k,k)^T
+		launch_gemm<KMAJOR, KMAJOR, EPI_STORE>(c, EMUB_K_GEMM_CHOL, 2.0 * TB * TB * TB * m->trsm_cnt[k], st, m->dTasks + m->trsm_off[k],
+		                                       m->trsm_cnt[k], count, A, m->mat, ld, W, m->mat, ld, A, m->mat, ld, 1.0);
+		// A(i,j) -= L(i,k) L(j,k)^T
+		launch_gemm<KMAJOR, KMAJOR, EPI_SUB>(c, EMUB_K_GEMM_CHOL, 2.0 * TB * TB * TB * m->syrk_cnt[k], st, m->dTasks + m->syrk_off[k],
+		                                     m->syrk_cnt[k], count, A, m->mat, ld, A, m->mat, ld, A, m->mat, ld, 1.0);
+	}
+}
+
+static void run_trtri(emub_model *m, cudaStream_t st, int s0, int count)
+{
+	emub_ctx *c = m->ctx;
+	const int ld = m->npad;
+	double *A = m->bufA + (size_t)s0 * m->mat, *W = m->bufW + (size_t)s0 * m->mat, *T = m->bufT + (size_t)s0 * m->mat;
+	for (const TrtriLevel &L : m->levels) {
+		launch_gemm<KMAJOR, RMAJOR, EPI_STORE>(c, EMUB_K_GEMM_TRTRI, L.flops1, st, m->dTasks + L.t1_off, L.t1_cnt, count, A, m->mat,
+		                                       ld, W, m->mat, ld, T, m->mat, ld, 1.0);
+		launch_gemm<KMAJOR, RMAJOR, EPI_STORE>(c, EMUB_K_GEMM_TRTRI, L.flops2, st, m->dTasks + L.t2_off, L.t2_cnt, count, W, m->mat,
+		                                       ld, T, m->mat, ld, W, m->mat, ld, -1.0);
+	}
+}
+
+static void run_lauum(emub_model *m, cudaStream_t st, int s0, int count)
+{
+	const int ld = m->npad;
+	double *A = m->bufA + (size_t)s0 * m->mat, *W = m->bufW + (size_t)s0 * m->mat;
+	launch_gemm<RMAJOR, RMAJOR, EPI_STORE>(m->ctx, EMUB_K_GEMM_LAUUM, m->lauum_flops, st, m->dTasks + m->lauum_off, m->lauum_cnt,
+	                                       count, W, m->mat, ld, W, m->mat, ld, A, m->mat, ld, 1.0);
+}
+
+// UG = W [y | H]; Gram partials; beta / sigma2 / -L
+static void run_regression(emub_model *m, cudaStream_t st, int s0, int count, int emulator_mode)
+{
+	emub_ctx *c = m->ctx;
+	const long long sUG = (long long)m->npad * m->ncp;
+	const int nchunk_cols = (m->p + 1 + 7) / 8;
+	double *W = m->bufW + (size_t)s0 * m->mat;
+	double *UG = m->dUG + (size_t)s0 * sUG;
+	{
+		LaunchScope ls(c, EMUB_K_SKINNY, count * 4.0 * (double)m->mat * nchunk_cols, st);
+		k_tri_rows_times<<<dim3(m->npad / 32, nchunk_cols, count), 256, 0, st>>>(W, (long long)m->mat, m->npad, m->dYh, 0, m->ncp, UG, sUG);
+	}
+	{
+		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
+		k_gram_partial<<<dim3(m->nblk, count), 256, (size_t)TB * m->ncp * sizeof(double), st>>>(
+		    UG, sUG, m->ncp, m->p + 1, m->dGramPart + (size_t)s0 * m->nblk * MAXNCP * MAXNCP, m->nblk);
+	}
+	{
+		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
+		k_small<<<count, 256, 0, st>>>(m->dGramPart + (size_t)s0 * m->nblk * MAXNCP * MAXNCP, m->nblk, UG, sUG, m->ncp, m->p, m->n,
+		                               m->npad, m->dLogdet + (size_t)s0 * m->nblk, m->nblk, m->dInfo + s0,
+		                               m->dRes + (size_t)s0 * RES_STRIDE, m->dConsts + (size_t)s0 * CONST_STRIDE, emulator_mode,
+		                               m->dMinv + (size_t)s0 * MAXNCP * MAXNCP);
+	}
+}
+
+// AB[:, first ncols8 chunks] = W^T UG
+static void run_wt_times(emub_model *m, cudaStream_t st, int s0, int count, int nchunk_cols)
+{
+	const long long sUG = (long long)m->npad * m->ncp;
+	LaunchScope ls(m->ctx, EMUB_K_SKINNY, count * 4.0 * (double)m->mat * nchunk_cols, st);
+	k_cols_times<true><<<dim3(m->npad / 32, nchunk_cols, count), 256, 0, st>>>(
+	    m->bufW + (size_t)s0 * m->mat, (long long)m->mat, m->npad, m->npad, m->dUG + (size_t)s0 * sUG, sUG, m->ncp,
+	    m->dAB + (size_t)s0 * sUG, sUG);
+}
+
+static void run_gradient(emub_model *m, cudaStream_t st, int s0, int count)
+{
+	emub_ctx *c = m->ctx;
+	const long long sUG = (long long)m->npad * m->ncp;
+	const int nt64 = m->npad / CT;
+	const size_t ntl = (size_t)nt64 * (nt64 + 1) / 2;
+	const size_t smem = (2 * (size_t)m->d * CT + 2 * CT) * sizeof(double);
+	double *Cinv = m->bufA + (size_t)s0 * m->mat;
+	double *AB = m->dAB + (size_t)s0 * sUG;
+	double *part = m->dGradPart + (size_t)s0 * ntl * MAXD;
+	const double *consts = m->dConsts + (size_t)s0 * CONST_STRIDE;
+	{
+		LaunchScope ls(c, EMUB_K_GRAD, count * 4.0 * (double)m->mat, st);
+		dim3 grid(nt64, nt64, count);
+		switch (m->kernel) {
+		case 2: k_grad_tiles<2><<<grid, 256, smem, st>>>(Cinv, (long long)m->mat, m->npad, AB, sUG, m->ncp, m->dX, m->n, m->d, consts, part, nt64); break;
+		case 3: k_grad_tiles<3><<<grid, 256, smem, st>>>(Cinv, (long long)m->mat, m->npad, AB, sUG, m->ncp, m->dX, m->n, m->d, consts, part, nt64); break;
+		default: k_grad_tiles<1><<<grid, 256, smem, st>>>(Cinv, (long long)m->mat, m->npad, AB, sUG, m->ncp, m->dX, m->n, m->d, consts, part, nt64); break;
+		}
+	}
+	{
+		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
+		k_grad_final<<<count, 256, 0, st>>>(part, nt64, Cinv, (long long)m->mat, m->npad, AB, sUG, m->ncp, m->n, m->d, m->kernel, consts,
+		                                    m->dRes + (size_t)s0 * RES_STRIDE);
+	}
+}
+
+// factorise + likelihood (+ gradient) for slots [s0, s0+count) whose thetas are already in dThetas
+static void run_group(emub_model *m, cudaStream_t st, int s0, int count, int nth_in, int mode, int want_grad, int emulator_mode)
+{
+	emub_ctx *c = m->ctx;
+	{
+		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
+		k_theta_prep<<<(count + 63) / 64, 64, 0, st>>>(m->dThetas + (size_t)s0 * nth_in, count, nth_in, m->kernel, m->d, mode,
+		                                               m->dConsts + (size_t)s0 * CONST_STRIDE);
+	}
+	cudaMemsetAsync(m->dInfo + s0, 0, sizeof(int) * count, st);
+	launch_cov(m, st, count, m->dConsts + (size_t)s0 * CONST_STRIDE, m->bufA + (size_t)s0 * m->mat, (long long)m->mat, 1);
+	run_cholesky(m, st, s0, count);
+	run_trtri(m, st, s0, count);
+	run_regression(m, st, s0, count, emulator_mode);
+	if (want_grad) {
+		run_lauum(m, st, s0, count);
+		run_wt_times(m, st, s0, count, 1);
+		run_gradient(m, st, s0, count);
+	}
+}
+
+// split `count` slots over the context's stream groups and run them concurrently
+static int run_chunk(emub_model *m, int count, int nth_in, int mode, int want_grad, int emulator_mode)
+{
+	emub_ctx *c = m->ctx;
+	int ng = c->profile ? 1 : std::min(c->ngroups, count);
+	// stream 0 is the entry/exit stream: fork to the other groups, join back
+	CUDA_TRY(cudaEventRecord(c->gev[0], c->streams[0]));
+	int s0 = 0;
+	for (int g = 0; g < ng; g++) {
+		int cnt = count / ng + (g < count % ng ? 1 : 0);
+		if (g > 0) CUDA_TRY(cudaStreamWaitEvent(c->streams[g], c->gev[0], 0));
+		run_group(m, c->streams[g], s0, cnt, nth_in, mode, want_grad, emulator_mode);
+		s0 += cnt;
+		if (g > 0) {
+			CUDA_TRY(cudaEventRecord(c->gev[g], c->streams[g]));
+			CUDA_TRY(cudaStreamWaitEvent(c->streams[0], c->gev[g], 0));
+		}
+	}
+	CUDA_TRY(cudaGetLastError());
+	m->last_count = count;
+	return EMUB_OK;
+}
+
+extern "C" int emub_loglik_grad_batch_dev(emub_model *m, const double *d_thetas, int B, int want_grad, double *d_out)
+{
+	if (!m || !d_thetas || !d_out || B < 0) return set_err(EMUB_EINVAL, "emub_loglik_grad_batch_dev: bad argument%s");
+	emub_ctx *c = m->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const int nth1 = m->nth - 1;
+	cudaStream_t st = c->streams[0];
+	for (int done = 0; done < B; done += m->nslots) {
+		const int count = std::min(m->nslots, B - done);
+		CUDA_TRY(cudaMemcpyAsync(m->dThetas, d_thetas + (size_t)done * nth1, sizeof(double) * count * nth1, cudaMemcpyDeviceToDevice, st));
+		int rc = run_chunk(m, count, nth1, THETA_LIK, want_grad, 0);
+		if (rc) return rc;
+		{
+			LaunchScope ls(c, EMUB_K_SMALL, 0, st);
+			k_pack_results<<<(count + 63) / 64, 64, 0, st>>>(m->dRes, count, nth1, d_out + (size_t)done * (nth1 + 4));
+		}
+	}
+	CUDA_TRY(cudaGetLastError());
+	return EMUB_OK;
+}
+
+extern "C" int emub_loglik_grad_batch(emub_model *m, const double *thetas, int B, int want_grad, double *negL, double *grad,
+                                      double *sigma2, int *status)
+{
+	if (!m || !thetas || B < 0) return set_err(EMUB_EINVAL, "emub_loglik_grad_batch: bad argument%s");
+	emub_ctx *c = m->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	const int nth1 = m->nth - 1;
+	cudaStream_t st = c->streams[0];
+	for (int done = 0; done < B; done += m->nslots) {
+		const int count = std::min(m->nslots, B - done);
+		memcpy(m->hThetas, thetas + (size_t)done * nth1, sizeof(double) * count * nth1);
+		CUDA_TRY(cudaMemcpyAsync(m->dThetas, m->hThetas, sizeof(double) * count * nth1, cudaMemcpyHostToDevice, st));
+		int rc = run_chunk(m, count, nth1, THETA_LIK, want_grad, 0);
+		if (rc) return rc;
+		CUDA_TRY(cudaMemcpyAsync(m->hRes, m->dRes, sizeof(double) * count * RES_STRIDE, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		for (int b = 0; b < count; b++) {
+			const double *r = m->hRes + (size_t)b * RES_STRIDE;
+			const int stt = (int)r[2];
+			if (negL) negL[done + b] = r[0];
+			if (sigma2) sigma2[done + b] = r[1];
+			if (status) status[done + b] = stt;
+			if (grad)
+				for (int k = 0; k < nth1; k++) grad[(size_t)(done + b) * nth1 + k] = (want_grad || stt) ? r[RES_GRAD + k] : 0.0;
+		}
+	}
+	return EMUB_OK;
+}
+
+extern "C" int emub_loglik_extras(emub_model *m, int b, double *logdet, double *beta)
+{
+	if (!m || b < 0 || b >= m->last_count) return set_err(EMUB_EINVAL, "emub_loglik_extras: bad slot%s");
+	const double *r = m->hRes + (size_t)b * RES_STRIDE;
+	if (logdet) *logdet = r[3];
+	if (beta) for (int c = 0; c < m->p; c++) beta[c] = r[RES_BETA + c];
+	return EMUB_OK;
+}
+
+// ---- compatibility entry points (not on the hot path) -------------------------------------------------
+extern "C" int emub_cov_matrix(emub_model *m, const double *thetas, double *C, int ldc)
+{
+	if (!m || !thetas || !C || ldc < m->n) return set_err(EMUB_EINVAL, "emub_cov_matrix: bad argument%s");
+	emub_ctx *c = m->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	cudaStream_t st = c->streams[0];
+	CUDA_TRY(cudaMemcpyAsync(m->dThetas, thetas, sizeof(double) * m->nth, cudaMemcpyHostToDevice, st));
+	{
+		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
+		k_theta_prep<<<1, 64, 0, st>>>(m->dThetas, 1, m->nth, m->kernel, m->d, THETA_FULL, m->dConsts);
+	}
+	launch_cov(m, st, 1, m->dConsts, m->bufT, (long long)m->mat, 0);
+	CUDA_TRY(cudaMemcpy2DAsync(C, sizeof(double) * ldc, m->bufT, sizeof(double) * m->npad, sizeof(double) * m->n, m->n,
+	                           cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(cudaGetLastError());
+	return EMUB_OK;
+}
+
+extern "C" int emub_h_matrix(emub_model *m, double *H, int ldh)
+{
+	if (!m || !H || ldh < m->p) return set_err(EMUB_EINVAL, "emub_h_matrix: bad argument%s");
+	CUDA_TRY(cudaSetDevice(m->ctx->device));
+	CUDA_TRY(cudaMemcpy2D(H, sizeof(double) * ldh, m->dYh + 1, sizeof(double) * m->ncp, sizeof(double) * m->p, m->n, cudaMemcpyDeviceToHost));
+	return EMUB_OK;
+}
+
+extern "C" int emub_k_vectors(emub_model *m, const double *thetas, const double *pts, int ldp, int mq, double *K, int ldk)
+{
+	if (!m || !thetas || !pts || !K || mq < 1 || ldp < m->d || ldk < mq) return set_err(EMUB_EINVAL, "emub_k_vectors: bad argument%s");
+	emub_ctx *c = m->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	cudaStream_t st = c->streams[0];
+	const int mq_pad = (mq + TB - 1) / TB * TB;
+	double *dQ = nullptr, *dK = nullptr;
+	CUDA_TRY(cudaMalloc(&dQ, sizeof(double) * (size_t)mq_pad * m->d));
+	CUDA_TRY(cudaMalloc(&dK, sizeof(double) * (size_t)m->npad * mq_pad));
+	CUDA_TRY(cudaMemcpy2DAsync(dQ, sizeof(double) * m->d, pts, sizeof(double) * ldp, sizeof(double) * m->d, mq, cudaMemcpyHostToDevice, st));
+	CUDA_TRY(cudaMemcpyAsync(m->dThetas, thetas, sizeof(double) * m->nth, cudaMemcpyHostToDevice, st));
+	{
+		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
+		k_theta_prep<<<1, 64, 0, st>>>(m->dThetas, 1, m->nth, m->kernel, m->d, THETA_FULL, m->dConsts);
+	}
+	launch_kcross(m, st, m->dConsts, dQ, mq, mq_pad, dK, mq_pad);
+	CUDA_TRY(cudaMemcpy2DAsync(K, sizeof(double) * ldk, dK, sizeof(double) * mq_pad, sizeof(double) * mq, m->n, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	cudaFree(dQ); cudaFree(dK);
+	CUDA_TRY(cudaGetLastError());
+	return EMUB_OK;
+}
+
+extern "C" int emub_debug_fetch(emub_model *m, int b, int which, double *out, int ldo)
+{
+	if (!m || !out || b < 0 || b >= m->nslots || ldo < m->n) return set_err(EMUB_EINVAL, "emub_debug_fetch: bad argument%s");
+	CUDA_TRY(cudaSetDevice(m->ctx->device));
+	CUDA_TRY(cudaDeviceSynchronize());
+	const double *src = (which == 0 ? m->bufA : (which == 1 ? m->bufW : m->bufT)) + (size_t)b * m->mat;
+	CUDA_TRY(cudaMemcpy2D(out, sizeof(double) * ldo, src, sizeof(double) * m->npad, sizeof(double) * m->n, m->n, cudaMemcpyDeviceToHost));
+	return EMUB_OK;
+}
+
+extern "C" int emub_debug_cholesky(emub_model *m, const double *theta_less_amp, double *L, int ldl, double *logdet)
+{
+	if (!m || !theta_less_amp || !L || ldl < m->n) return set_err(EMUB_EINVAL, "emub_debug_cholesky: bad argument%s");
+	emub_ctx *c = m->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	cudaStream_t st = c->streams[0];
+	const int nth1 = m->nth - 1;
+	CUDA_TRY(cudaMemcpyAsync(m->dThetas, theta_less_amp, sizeof(double) * nth1, cudaMemcpyHostToDevice, st));
+	{
+		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
+		k_theta_prep<<<1, 64, 0, st>>>(m->dThetas, 1, nth1, m->kernel, m->d, THETA_LIK, m->dConsts);
+	}
+	CUDA_TRY(cudaMemsetAsync(m->dInfo, 0, sizeof(int), st));
+	launch_cov(m, st, 1, m->dConsts, m->bufA, (long long)m->mat, 1);
+	run_cholesky(m, st, 0, 1);
+	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpy2D(L, sizeof(double) * ldl, m->bufA, sizeof(double) * m->npad, sizeof(double) * m->n, m->n, cudaMemcpyDeviceToHost));
+	std::vector<double> parts(m->nblk);
+	int info = 0;
+	CUDA_TRY(cudaMemcpy(parts.data(), m->dLogdet, sizeof(double) * m->nblk, cudaMemcpyDeviceToHost));
+	CUDA_TRY(cudaMemcpy(&info, m->dInfo, sizeof(int), cudaMemcpyDeviceToHost));
+	double s = 0;
+	for (double v : parts) s += v;
+	if (logdet) *logdet = 2.0 * s;
+	// zero the strictly upper part for the caller (upper off-diagonal tiles are never written)
+	for (int i = 0; i < m->n; i++) for (int j = i + 1; j < m->n; j++) L[(size_t)i * ldl + j] = 0.0;
+	return info ? EMUB_EDOM : EMUB_OK;
+}
+
+// ---- prediction ------------------------------------------------------------------------------------------
+extern "C" int emub_emulator_create(emub_model *m, const double *thetas, emub_emulator **out)
+{
+	if (!m || !thetas || !out) return set_err(EMUB_EINVAL, "emub_emulator_create: null%s");
+	emub_ctx *c = m->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	cudaStream_t st = c->streams[0];
+	CUDA_TRY(cudaMemcpyAsync(m->dThetas, thetas, sizeof(double) * m->nth, cudaMemcpyHostToDevice, st));
+	// factorise in slot 0 on stream 0 only
+	const int saved_groups = c->ngroups;
+	c->ngroups = 1;
+	int rc = run_chunk(m, 1, m->nth, THETA_FULL, 0, 1);
+	c->ngroups = saved_groups;
+	if (rc) return rc;
+	run_wt_times(m, st, 0, 1, (m->p + 1 + 7) / 8);
+	CUDA_TRY(cudaMemcpyAsync(m->hRes, m->dRes, sizeof(double) * RES_STRIDE, cudaMemcpyDeviceToHost, st));
+	double hc[4];
+	CUDA_TRY(cudaMemcpyAsync(hc, m->dConsts, sizeof(hc), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(cudaGetLastError());
+	const int status = (int)m->hRes[2];
+	if (status == 1) return set_err(EMUB_EDOM, "emub_emulator_create: covariance matrix not positive definite%s");
+	if (status == 2) return set_err(EMUB_EREG, "emub_emulator_create: regression matrix not positive definite%s");
+	emub_emulator *e = new emub_emulator();
+	memset(e, 0, sizeof(*e));
+	e->m = m;
+	e->kappa = hc[0] + hc[1];  // c(x*, x*) = amp + nugget   (emulator_struct.c:135)
+	for (int i = 0; i < m->p; i++) e->hbeta[i] = m->hRes[RES_BETA + i];
+	const size_t sUG = (size_t)m->npad * m->ncp;
+	CUDA_TRY(cudaMalloc(&e->W, m->mat * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&e->AB, sUG * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&e->beta, MAXNCP * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&e->Minv, MAXNCP * MAXNCP * sizeof(double)));
+	CUDA_TRY(cudaMalloc(&e->consts, CONST_STRIDE * sizeof(double)));
+	CUDA_TRY(cudaMemcpyAsync(e->W, m->bufW, m->mat * sizeof(double), cudaMemcpyDeviceToDevice, st));
+	CUDA_TRY(cudaMemcpyAsync(e->AB, m->dAB, sUG * sizeof(double), cudaMemcpyDeviceToDevice, st));
+	CUDA_TRY(cudaMemcpyAsync(e->beta, m->dRes + RES_BETA, MAXNCP * sizeof(double), cudaMemcpyDeviceToDevice, st));
+	CUDA_TRY(cudaMemcpyAsync(e->Minv, m->dMinv, MAXNCP * MAXNCP * sizeof(double), cudaMemcpyDeviceToDevice, st));
+	CUDA_TRY(cudaMemcpyAsync(e->consts, m->dConsts, CONST_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, st));
+	// query workspace: chunk of up to 16384 points, K (npad x mqc) bounded to ~1 GiB
+	int mqc = 16384;
+	while (mqc > TB && (size_t)m->npad * mqc * sizeof(double) > ((size_t)1 << 30)) mqc /= 2;
+	e->mqc = mqc;
+	CUDA_TRY(cudaMalloc(&e->dQ, sizeof(double) * (size_t)mqc * m->d));
+	CUDA_TRY(cudaMalloc(&e->dK, sizeof(double) * (size_t)m->npad * mqc));
+	CUDA_TRY(cudaMalloc(&e->dVsq, sizeof(double) * (size_t)m->nblk * mqc));
+	CUDA_TRY(cudaMalloc(&e->dKA, sizeof(double) * (size_t)mqc * m->ncp));
+	CUDA_TRY(cudaMalloc(&e->dMean, sizeof(double) * mqc));
+	CUDA_TRY(cudaMalloc(&e->dVar, sizeof(double) * mqc));
+	CUDA_TRY(cudaMallocHost(&e->hQ, sizeof(double) * (size_t)mqc * m->d));
+	CUDA_TRY(cudaMallocHost(&e->hOut, sizeof(double) * 2 * mqc));
+	// V = W K, one task per row block (longest K first); the batch dimension walks the query blocks
+	std::vector<GemmTask> tasks;
+	for (int i = m->nblk - 1; i >= 0; i--) tasks.push_back({(long long)i * TB * m->npad, 0, 0, (i + 1) * TB, i});
+	CUDA_TRY(cudaMalloc(&e->dTasks, tasks.size() * sizeof(GemmTask)));
+	CUDA_TRY(cudaMemcpyAsync(e->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	*out = e;
+	return EMUB_OK;
+}
+
+extern "C" void emub_emulator_destroy(emub_emulator *e)
+{
+	if (!e) return;
+	cudaSetDevice(e->m->ctx->device);
+	cudaDeviceSynchronize();
+	cudaFree(e->W); cudaFree(e->AB); cudaFree(e->beta); cudaFree(e->Minv); cudaFree(e->consts);
+	cudaFree(e->dQ); cudaFree(e->dK); cudaFree(e->dVsq); cudaFree(e->dKA); cudaFree(e->dMean); cudaFree(e->dVar); cudaFree(e->dTasks);
+	cudaFreeHost(e->hQ); cudaFreeHost(e->hOut);
+	delete e;
+}
+
+extern "C" int emub_emulator_beta(emub_emulator *e, double *beta)
+{
+	if (!e || !beta) return EMUB_EINVAL;
+	for (int i = 0; i < e->m->p; i++) beta[i] = e->hbeta[i];
+	return EMUB_OK;
+}
+
+// one chunk (mq <= mqc) whose points are already at dQ (contiguous mq x d)
+static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, int mq, double *dMean, double *dVar)
+{
+	emub_model *m = e->m;
+	emub_ctx *c = m->ctx;
+	const int mq_pad = (mq + TB - 1) / TB * TB;
+	const int ldk = e->mqc;
+	launch_kcross(m, st, e->consts, dQ, mq, mq_pad, e->dK, ldk);
+	const int nqb = mq_pad / TB;
+	// |W k|^2 partials: tile (row block i, query block qb)
+	launch_gemm<KMAJOR, RMAJOR, EPI_COLSUMSQ>(c, EMUB_K_GEMM_PRED, (double)m->npad * (m->npad + TB) * TB, st, e->dTasks, m->nblk, nqb,
+	                                          e->W, 0, m->npad, e->dK, TB, ldk, e->dVsq, TB, ldk, 1.0);
+	{
+		const int nchunk_cols = (m->p + 1 + 7) / 8;
+		LaunchScope ls(c, EMUB_K_SKINNY, 8.0 * (double)m->npad * mq_pad * nchunk_cols, st);
+		k_cols_times<false><<<dim3(mq_pad / 32, nchunk_cols, 1), 256, 0, st>>>(e->dK, 0, ldk, m->npad, e->AB, 0, m->ncp, e->dKA, 0);
+	}
+	{
+		LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);
+		k_pred_final<<<(mq + 127) / 128, 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, e->dKA, m->ncp, e->dVsq, m->nblk, ldk, e->beta,
+		                                               e->Minv, e->kappa, dMean, dVar);
+	}
+	CUDA_TRY(cudaGetLastError());
+	return EMUB_OK;
+}
+
+extern "C" int emub_predict_batch_dev(emub_emulator *e, const double *d_pts, int mq, double *d_mean, double *d_var)
+{
+	if (!e || !d_pts || !d_mean || !d_var || mq < 0) return set_err(EMUB_EINVAL, "emub_predict_batch_dev: bad argument%s");
+	emub_model *m = e->m;
+	CUDA_TRY(cudaSetDevice(m->ctx->device));
+	cudaStream_t st = m->ctx->streams[0];
+	for (int done = 0; done < mq; done += e->mqc) {
+		const int cnt = std::min(e->mqc, mq - done);
+		int rc = predict_chunk(e, st, d_pts + (size_t)done * m->d, cnt, d_mean + done, d_var + done);
+		if (rc) return rc;
+	}
+	return EMUB_OK;
+}
+
+extern "C" int emub_predict_batch(emub_emulator *e, const double *pts, int ldp, int mq, double *mean, double *var)
+{
+	if (!e || !pts || !mean || !var || mq < 0 || ldp < e->m->d) return set_err(EMUB_EINVAL, "emub_predict_batch: bad argument%s");
+	emub_model *m = e->m;
+	CUDA_TRY(cudaSetDevice(m->ctx->device));
+	cudaStream_t st = m->ctx->streams[0];
+	for (int done = 0; done < mq; done += e->mqc) {
+		const int cnt = std::min(e->mqc, mq - done);
+		for (int q = 0; q < cnt; q++) memcpy(e->hQ + (size_t)q * m->d, pts + (size_t)(done + q) * ldp, sizeof(double) * m->d);
+		CUDA_TRY(cudaMemcpyAsync(e->dQ, e->hQ, sizeof(double) * (size_t)cnt * m->d, cudaMemcpyHostToDevice, st));
+		int rc = predict_chunk(e, st, e->dQ, cnt, e->dMean, e->dVar);
+		if (rc) return rc;
+		CUDA_TRY(cudaMemcpyAsync(e->hOut, e->dMean, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaMemcpyAsync(e->hOut + e->mqc, e->dVar, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaStreamSynchronize(st));
+		memcpy(mean + done, e->hOut, sizeof(double) * cnt);
+		memcpy(var + done, e->hOut + e->mqc, sizeof(double) * cnt);
+	}
+	return EMUB_OK;
+}

@@ -1,0 +1,685 @@
+// emub_kernels.cuh -- the non-GEMM kernels of the engine: theta preparation, covariance
+// construction (K1), regression basis, diagonal-block factorisation (POTF2 + in-place triangular
+// inverse), skinny products against W = L^-1, the small p x p regression algebra (K6), the fused
+// likelihood-gradient reduction (K4) and the prediction epilogue.
+// Reference formulas are cited as file:line under the reference's src/.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "emub_gemm.cuh"
+
+namespace emub {
+
+constexpr int MAXD = 32;     // nparams limit (smem staging of design rows)
+constexpr int MAXNCP = 48;   // 1 + nregression_fns, padded to a multiple of 8
+constexpr int CT = 64;       // covariance / gradient tile edge
+
+// per-point constants derived from theta, layout (stride CONST_STRIDE doubles):
+//  [0] amp  [1] nugget  [2] rho (Matern)  [3] sigma2 slot (filled later)
+//  [4 .. 4+d)       1 / (exp(theta_k))^2               emulator.c:123-127
+//  [4+d .. 4+2d)    0.5 * exp(-2 theta_k)              emulator.c:181,203
+//  [4+2d .. 4+3d)   exp(-2 theta_k)
+constexpr int CONST_STRIDE = 4 + 3 * MAXD;
+
+enum { THETA_LIK = 0 /* theta without amplitude, unit amplitude (maxmultimin.c:311-313; Matern: D-2) */,
+       THETA_FULL = 1 /* literal full vector (emulator_struct.c:28) */ };
+
+__global__ void k_theta_prep(const double *__restrict__ thetas, int B, int nth_in, int kernel, int d, int mode,
+                             double *__restrict__ consts)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= B) return;
+	const double *th = thetas + (size_t)b * nth_in;
+	double *c = consts + (size_t)b * CONST_STRIDE;
+	if (kernel == 1) {
+		const double *len;
+		if (mode == THETA_LIK) { c[0] = 1.0; c[1] = exp(th[0]); len = th + 1; }
+		else { c[0] = exp(th[0]); c[1] = exp(th[1]); len = th + 2; }
+		c[2] = 0.0;
+		for (int k = 0; k < d; k++) {
+			double r = exp(len[k]);
+			r = r * r;
+			c[4 + k] = 1.0 / r;
+			double e2 = exp(-2.0 * len[k]);
+			c[4 + d + k] = 0.5 * e2;
+			c[4 + 2 * d + k] = e2;
+		}
+	} else {
+		if (mode == THETA_LIK) { c[0] = 1.0; c[1] = exp(th[0]); c[2] = exp(th[1]); }
+		else { c[0] = th[0]; c[1] = th[1]; c[2] = exp(th[2]); }
+	}
+	c[3] = 0.0;
+}
+
+// ---- covariance pair functions (literal operation order of the reference) -------------------------
+template <int KERNEL>
+__device__ __forceinline__ double cov_pair(const double *xi, int si, const double *xj, int sj, int d,
+                                           const double *__restrict__ c)
+{
+	if (KERNEL == 1) {
+		// emulator.c:101-152
+		double e = 0.0;
+		int cnt = 0;
+		for (int k = 0; k < d; k++) {
+			double dist = fabs(xi[k * si] - xj[k * sj]);
+			e += ((-0.5 * dist) * dist) * c[4 + k];
+			cnt += (dist < 0.0000000001);
+		}
+		double v = exp(e) * c[0];
+		if (cnt == d) v += c[1];
+		return v;
+	} else {
+		// emulator.c:344-386 (Matern 3/2), :438-480 (Matern 5/2)
+		double r2 = 0.0;
+		int cnt = 0;
+		for (int k = 0; k < d; k++) {
+			double dist = fabs(xi[k * si] - xj[k * sj]);
+			r2 += dist * dist;
+			cnt += (dist < 0.0000000000000001);
+		}
+		double dist = sqrt(r2);
+		double v;
+		if (KERNEL == 2) {
+			const double root3 = 1.732050808;
+			if (dist > 0.0) v = c[0] * (1 + root3 * (dist / c[2])) * exp(-root3 * (dist / c[2]));
+			else v = c[0];
+		} else {
+			const double root5 = 2.236067978;
+			double dr = dist / c[2];
+			if (dist > 0.0) v = c[0] * (1 + root5 * dr + (5.0 / 3.0) * dr * dr) * exp(-root5 * dr);
+			else v = c[0];
+		}
+		if (cnt == d) v += c[1];
+		return v;
+	}
+}
+
+// K1.  grid (ceil(ncols/64), ceil(nrows/64), B), 256 threads, dynamic smem 2*d*64 doubles.
+// Square mode (CROSS=false): rows and columns are design points; entries outside n x n are the identity
+// (padding); lower_only skips tiles strictly above the diagonal.
+// Cross mode: columns are query points (mq valid), clamp < 1e-10 -> 0 (emulator.c:588-590), padding is 0.
+template <int KERNEL, bool CROSS>
+__global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n, int d, const double *__restrict__ Q,
+                                             int mq, const double *__restrict__ consts, long long const_stride,
+                                             double *__restrict__ out, long long out_stride, int ld, int lower_only)
+{
+	const int bj = blockIdx.x, bi = blockIdx.y, b = blockIdx.z;
+	if (!CROSS && lower_only && bj > bi) return;
+	extern __shared__ double sm[];
+	double *sXi = sm;            // [d][64]
+	double *sXj = sm + d * CT;   // [d][64]
+	__shared__ double sc[CONST_STRIDE];
+	const int tid = threadIdx.x;
+	const double *cg = consts + b * const_stride;
+	for (int i = tid; i < 4 + 3 * d; i += 256) sc[i] = cg[i];
+	const int i0 = bi * CT, j0 = bj * CT;
+	const int ncols = CROSS ? mq : n;
+	const double *XJ = CROSS ? Q : X;
+	for (int idx = tid; idx < CT * d; idx += 256) {
+		int r = idx / d, k = idx - r * d;
+		sXi[k * CT + r] = (i0 + r < n) ? X[(size_t)(i0 + r) * d + k] : 0.0;
+		sXj[k * CT + r] = (j0 + r < ncols) ? XJ[(size_t)(j0 + r) * d + k] : 0.0;
+	}
+	__syncthreads();
+	const int tx = tid & 15, ty = tid >> 4;
+	double *o = out + b * out_stride;
+#pragma unroll
+	for (int r = 0; r < 4; r++) {
+		const int li = ty + 16 * r, gi = i0 + li;
+#pragma unroll
+		for (int c = 0; c < 4; c++) {
+			const int lj = tx + 16 * c, gj = j0 + lj;
+			double v;
+			if (gi < n && gj < ncols) {
+				v = cov_pair<KERNEL>(sXi + li, CT, sXj + lj, CT, d, sc);
+				if (CROSS && v < 1E-10) v = 0.0;
+			} else {
+				v = (!CROSS && gi == gj) ? 1.0 : 0.0;
+			}
+			o[(size_t)gi * ld + gj] = v;
+		}
+	}
+}
+
+// Yh = [ y | H | 0 ] (npad x ncp), H per regression.c:9-67; rows >= n are zero.
+__global__ void k_build_yh(const double *__restrict__ X, const double *__restrict__ y, int n, int npad, int d, int order,
+                           int ncp, double *__restrict__ Yh)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= npad) return;
+	double *row = Yh + (size_t)i * ncp;
+	for (int c = 0; c < ncp; c++) row[c] = 0.0;
+	if (i >= n) return;
+	row[0] = y[i];
+	row[1] = 1.0;
+	const double *x = X + (size_t)i * d;
+	if (order >= 1) for (int k = 0; k < d; k++) row[2 + k] = x[k];
+	if (order >= 2) for (int k = 0; k < d; k++) row[2 + d + k] = x[k] * x[k];
+	if (order >= 3) for (int k = 0; k < d; k++) row[2 + 2 * d + k] = x[k] * x[k] * x[k];
+}
+__global__ void k_set_y(const double *__restrict__ y, int n, int ncp, double *__restrict__ Yh)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) Yh[(size_t)i * ncp] = y[i];
+}
+
+// ---- POTF2: Cholesky of one 128 x 128 diagonal block + its triangular inverse, in shared memory ----
+// Right-looking column sweep.  The same row operations that reduce A to L are applied to the identity
+// (stored in the slots of the already eliminated columns), so after the sweep the lower triangle holds
+// L^-1; the finished columns of L are stashed transposed in the unused upper triangle.
+// grid (B), 256 threads, dynamic smem (128*129 + 3*128) doubles.
+constexpr int POTF2_THREADS = 256;
+constexpr int PS = TB + 1;
+constexpr int POTF2_SMEM_BYTES = (TB * PS + 3 * TB) * 8;
+
+__global__ void __launch_bounds__(POTF2_THREADS) k_potf2(double *Abase, long long strideA, double *Wbase, long long strideW,
+                                                         int ld, int kblk, int nblk, double *__restrict__ logdet_parts,
+                                                         int *__restrict__ info)
+{
+	extern __shared__ double sm[];
+	double *S = sm;
+	double *lcol = S + TB * PS;
+	double *vrow = lcol + TB;
+	double *ldiag = vrow + TB;
+	const int tid = threadIdx.x, b = blockIdx.x;
+	const int warp = tid >> 5, lane = tid & 31;
+	double *A = Abase + b * strideA + (size_t)kblk * TB * ld + (size_t)kblk * TB;
+	double *W = Wbase + b * strideW + (size_t)kblk * TB * ld + (size_t)kblk * TB;
+	for (int idx = tid; idx < TB * TB; idx += POTF2_THREADS) {
+		int i = idx >> 7, c = idx & 127;
+		S[i * PS + c] = (c <= i) ? A[(size_t)i * ld + c] : 0.0;
+	}
+	__syncthreads();
+	double logsum = 0.0;
+	int bad = 0;
+	for (int j = 0; j < TB; j++) {
+		const double ajj = S[j * PS + j];
+		const bool ok = (ajj > 0.0) && (ajj < 1.0e300);
+		if (!ok) bad = 1;
+		const double ljj = sqrt(ok ? ajj : 1.0);
+		const double inv = 1.0 / ljj;
+		if (tid == 0) logsum += log(ljj);
+		if (tid < TB) {
+			const int i = tid;
+			if (i > j) {
+				double l = S[i * PS + j] * inv;
+				lcol[i] = l;
+				S[j * PS + i] = l;  // stash L(i, j) transposed
+			} else if (i == j) {
+				ldiag[j] = ljj;
+			}
+		} else {
+			const int c = tid - TB;
+			if (c < j) {
+				double e = S[j * PS + c] * inv;
+				vrow[c] = e;
+			} else if (c == j) {
+				vrow[j] = inv;
+			}
+		}
+		__syncthreads();
+		// row j of the inverse becomes final; rows i > j get  S(i, c) -= L(i, j) * v(c)
+		if (tid <= j) S[j * PS + tid] = vrow[tid];
+		for (int i = j + 1 + warp; i < TB; i += POTF2_THREADS / 32) {
+			const double li = lcol[i];
+			double *Si = S + i * PS;
+			for (int c = lane; c <= i; c += 32) {
+				if (c < j) Si[c] -= li * vrow[c];
+				else if (c == j) Si[c] = -li * vrow[j];
+				else Si[c] -= li * lcol[c];
+			}
+		}
+		__syncthreads();
+	}
+	if (tid == 0) {
+		logdet_parts[(size_t)b * nblk + kblk] = logsum;
+		if (bad) info[b] = 1;
+	}
+	for (int idx = tid; idx < TB * TB; idx += POTF2_THREADS) {
+		int i = idx >> 7, c = idx & 127;
+		double l, w;
+		if (c < i) { l = S[c * PS + i]; w = S[i * PS + c]; }
+		else if (c == i) { l = ldiag[i]; w = S[i * PS + i]; }
+		else { l = 0.0; w = 0.0; }
+		A[(size_t)i * ld + c] = l;
+		W[(size_t)i * ld + c] = w;
+	}
+}
+
+// ---- skinny products ---------------------------------------------------------------------------------
+// (a) OUT[i][c0..c0+8) = sum_{j <= i} W[i][j] * V[j][c0..c0+8)   (W lower triangular, npad x npad)
+// grid (npad/32, ncp/8, B), 256 threads: one warp per 4 rows.
+__global__ void __launch_bounds__(256) k_tri_rows_times(const double *__restrict__ Wbase, long long strideW, int ld,
+                                                        const double *__restrict__ Vbase, long long strideV, int ncp,
+                                                        double *__restrict__ Obase, long long strideO)
+{
+	const int b = blockIdx.z, c0 = blockIdx.y * 8;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int r0 = blockIdx.x * 32 + warp * 4;
+	const double *W = Wbase + b * strideW;
+	const double *V = Vbase + b * strideV;
+	double acc[4][8];
+#pragma unroll
+	for (int r = 0; r < 4; r++)
+#pragma unroll
+		for (int c = 0; c < 8; c++) acc[r][c] = 0.0;
+	const int jmax = r0 + 3;
+	for (int j = lane; j <= jmax; j += 32) {
+		const double4 v0 = *reinterpret_cast<const double4 *>(V + (size_t)j * ncp + c0);
+		const double4 v1 = *reinterpret_cast<const double4 *>(V + (size_t)j * ncp + c0 + 4);
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			const double w = (j <= r0 + r) ? W[(size_t)(r0 + r) * ld + j] : 0.0;
+			acc[r][0] += w * v0.x; acc[r][1] += w * v0.y; acc[r][2] += w * v0.z; acc[r][3] += w * v0.w;
+			acc[r][4] += w * v1.x; acc[r][5] += w * v1.y; acc[r][6] += w * v1.z; acc[r][7] += w * v1.w;
+		}
+	}
+#pragma unroll
+	for (int r = 0; r < 4; r++)
+#pragma unroll
+		for (int c = 0; c < 8; c++) {
+			double s = acc[r][c];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+			acc[r][c] = s;
+		}
+	if (lane < 4) {
+		double *O = Obase + b * strideO + (size_t)(r0 + lane) * ncp + c0;
+#pragma unroll
+		for (int r = 0; r < 4; r++)
+			if (lane == r)
+#pragma unroll
+				for (int c = 0; c < 8; c++) O[c] = acc[r][c];
+	}
+}
+
+// (b) OUT[j][c0..c0+8) = sum_{i >= ibegin(j)} M[i][j] * V[i][c0..c0+8)
+// TRI: M = W lower triangular (i >= j); otherwise all nrows rows (M = K, n x mq).
+// grid (ncols/32, ncp/8, B), 256 threads: lanes = 32 consecutive columns, warps stride over rows.
+template <bool TRI>
+__global__ void __launch_bounds__(256) k_cols_times(const double *__restrict__ Mbase, long long strideM, int ld, int nrows,
+                                                    const double *__restrict__ Vbase, long long strideV, int ncp,
+                                                    double *__restrict__ Obase, long long strideO)
+{
+	__shared__ double red[8][32][9];
+	const int b = blockIdx.z, c0 = blockIdx.y * 8;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int j0 = blockIdx.x * 32, j = j0 + lane;
+	const double *M = Mbase + b * strideM;
+	const double *V = Vbase + b * strideV;
+	double acc[8];
+#pragma unroll
+	for (int c = 0; c < 8; c++) acc[c] = 0.0;
+	const int ibeg = TRI ? j0 : 0;
+#pragma unroll 4
+	for (int i = ibeg + warp; i < nrows; i += 8) {
+		double m = M[(size_t)i * ld + j];
+		if (TRI && i < j) m = 0.0;
+		const double4 v0 = *reinterpret_cast<const double4 *>(V + (size_t)i * ncp + c0);
+		const double4 v1 = *reinterpret_cast<const double4 *>(V + (size_t)i * ncp + c0 + 4);
+		acc[0] += m * v0.x; acc[1] += m * v0.y; acc[2] += m * v0.z; acc[3] += m * v0.w;
+		acc[4] += m * v1.x; acc[5] += m * v1.y; acc[6] += m * v1.z; acc[7] += m * v1.w;
+	}
+#pragma unroll
+	for (int c = 0; c < 8; c++) red[warp][lane][c] = acc[c];
+	__syncthreads();
+	{
+		const int l = threadIdx.x >> 3, c = threadIdx.x & 7;
+		double s = 0.0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) s += red[w][l][c];
+		Obase[b * strideO + (size_t)(j0 + l) * ncp + c0 + c] = s;
+	}
+}
+
+// ---- Gram partials: G_part[b][chunk][c1][c2] = sum_{r in chunk} UG[r][c1] UG[r][c2] ----------------
+// grid (npad/128, B), 256 threads, dynamic smem 128*ncp doubles
+__global__ void __launch_bounds__(256) k_gram_partial(const double *__restrict__ UGbase, long long strideUG, int ncp, int nc,
+                                                      double *__restrict__ part, int nchunks)
+{
+	extern __shared__ double sm[];
+	const int b = blockIdx.y, ch = blockIdx.x;
+	const double *UG = UGbase + b * strideUG + (size_t)ch * TB * ncp;
+	for (int idx = threadIdx.x; idx < TB * ncp; idx += 256) sm[idx] = UG[idx];
+	__syncthreads();
+	double *o = part + ((size_t)b * nchunks + ch) * (MAXNCP * MAXNCP);
+	for (int idx = threadIdx.x; idx < nc * nc; idx += 256) {
+		int c1 = idx / nc, c2 = idx - c1 * nc;
+		double s = 0.0;
+		for (int r = 0; r < TB; r++) s += sm[r * ncp + c1] * sm[r * ncp + c2];
+		o[c1 * MAXNCP + c2] = s;
+	}
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double *scratch /* >= 8 */)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double s = 0.0;
+#pragma unroll
+	for (int w = 0; w < 8; w++) s += scratch[w];
+	return s;
+}
+
+// per-point results, stride RES_STRIDE doubles:
+//  [0] negL [1] sigma2 [2] status [3] logdet [4] u.z [5] z.z [6] tr(Cinv) [7] alpha.alpha
+//  [8 .. 8+MAXNCP) beta   [8+MAXNCP ..) gradient (nthetas-1)
+constexpr int RES_BETA = 8;
+constexpr int RES_GRAD = 8 + MAXNCP;
+constexpr int RES_STRIDE = RES_GRAD + MAXD + 2;
+
+// K6 + likelihood scalar.  One CTA (256 threads) per point.
+//  S = sum of Gram partials;  beta = (G^T G)^-1 G^T u  (regression.c:120-176 with C^-1 = W^T W);
+//  z = u - G beta = W (y - H beta);  sigma2 = u.z / n (maxmultimin.c:259-263);
+//  -L = 0.5 logdet + (n/2) 1.83788 + 0.5 z.z  (estimator-fns.c:48,85-95; logdet per D-1)
+// emulator mode: additionally Minv = (G^T G)^-1 (emulator.c:745-769) and UG[:,0] <- z.
+__global__ void __launch_bounds__(256) k_small(const double *__restrict__ part, int nchunks, double *UGbase, long long strideUG,
+                                               int ncp, int p, int n, int npad, const double *__restrict__ logdet_parts, int nblk,
+                                               const int *__restrict__ info, double *__restrict__ res,
+                                               double *__restrict__ consts, int emulator_mode, double *__restrict__ Minv)
+{
+	__shared__ double S[MAXNCP][MAXNCP + 1];
+	__shared__ double Lm[MAXNCP][MAXNCP + 1];
+	__shared__ double beta[MAXNCP];
+	__shared__ double scratch[8];
+	__shared__ int regbad;
+	const int b = blockIdx.x, tid = threadIdx.x;
+	const int nc = p + 1;
+	double *UG = UGbase + b * strideUG;
+	double *r = res + (size_t)b * RES_STRIDE;
+	for (int idx = tid; idx < nc * nc; idx += 256) {
+		int c1 = idx / nc, c2 = idx - c1 * nc;
+		double s = 0.0;
+		for (int ch = 0; ch < nchunks; ch++) s += part[((size_t)b * nchunks + ch) * (MAXNCP * MAXNCP) + c1 * MAXNCP + c2];
+		S[c1][c2] = s;
+	}
+	if (tid == 0) regbad = 0;
+	__syncthreads();
+	// Cholesky of D = S[1..p][1..p] by warp 0 (p <= 47: lanes own rows i and i + 32)
+	if (tid < 32) {
+		for (int i = tid; i < p; i += 32)
+			for (int c = 0; c < p; c++) Lm[i][c] = S[1 + i][1 + c];
+		__syncwarp();
+		for (int j = 0; j < p; j++) {
+			double djj = Lm[j][j];
+			if (!(djj > 0.0)) { if (tid == 0) regbad = 1; djj = 1.0; }
+			double ljj = sqrt(djj);
+			__syncwarp();
+			for (int i = tid; i < p; i += 32) {
+				if (i == j) Lm[j][j] = ljj;
+				else if (i > j) Lm[i][j] = Lm[i][j] / ljj;
+			}
+			__syncwarp();
+			for (int i = j + 1 + tid; i < p; i += 32) {
+				double lij = Lm[i][j];
+				for (int c = j + 1; c <= i; c++) Lm[i][c] -= lij * Lm[c][j];
+			}
+			__syncwarp();
+		}
+		// solve D beta = G^T u  (S[1+i][0])
+		if (tid == 0) {
+			for (int i = 0; i < p; i++) {
+				double s = S[1 + i][0];
+				for (int c = 0; c < i; c++) s -= Lm[i][c] * beta[c];
+				beta[i] = s / Lm[i][i];
+			}
+			for (int i = p - 1; i >= 0; i--) {
+				double s = beta[i];
+				for (int c = i + 1; c < p; c++) s -= Lm[c][i] * beta[c];
+				beta[i] = s / Lm[i][i];
+			}
+		}
+		if (emulator_mode) {
+			// Minv column by column: lane c solves D x = e_c
+			__syncwarp();
+			for (int c = tid; c < p; c += 32) {
+				double x[MAXNCP];
+				for (int i = 0; i < p; i++) {
+					double s = (i == c) ? 1.0 : 0.0;
+					for (int k = 0; k < i; k++) s -= Lm[i][k] * x[k];
+					x[i] = s / Lm[i][i];
+				}
+				for (int i = p - 1; i >= 0; i--) {
+					double s = x[i];
+					for (int k = i + 1; k < p; k++) s -= Lm[k][i] * x[k];
+					x[i] = s / Lm[i][i];
+				}
+				for (int i = 0; i < p; i++) Minv[(size_t)b * MAXNCP * MAXNCP + i * MAXNCP + c] = x[i];
+			}
+		}
+	}
+	__syncthreads();
+	double uz = 0.0, zz = 0.0;
+	for (int i = tid; i < npad; i += 256) {
+		const double *row = UG + (size_t)i * ncp;
+		double u = row[0];
+		double z = u;
+		for (int c = 0; c < p; c++) z -= row[1 + c] * beta[c];
+		uz += u * z;
+		zz += z * z;
+		if (emulator_mode) UG[(size_t)i * ncp] = z;
+	}
+	uz = block_sum_256(uz, scratch);
+	zz = block_sum_256(zz, scratch);
+	if (tid == 0) {
+		double logdet = 0.0;
+		for (int k = 0; k < nblk; k++) logdet += logdet_parts[(size_t)b * nblk + k];
+		logdet *= 2.0;
+		const double sigma2 = uz / (double)n;
+		const double log_2_pi = 1.83788;  // estimator-fns.c:48 (truncated literal)
+		double L = -(1.0 / 2.0) * logdet - (n / 2.0) * log_2_pi;
+		L += zz * (-1.0 / 2.0);
+		int status = info[b] ? 1 : (regbad ? 2 : 0);
+		r[0] = status ? nan("") : -1.0 * L;
+		r[1] = status ? nan("") : sigma2;
+		r[2] = (double)status;
+		r[3] = logdet;
+		r[4] = uz;
+		r[5] = zz;
+		for (int c = 0; c < p; c++) r[RES_BETA + c] = beta[c];
+		consts[(size_t)b * CONST_STRIDE + 3] = sigma2;
+	}
+}
+
+// ---- K4: fused gradient reduction ---------------------------------------------------------------------
+// part[b][tile][k] = sum over strictly-lower pairs (i > j) of the 64 x 64 tile of
+//      (alpha_i alpha_j - Cinv_ij) * q_k * exp(-a_k q_k),   q_k = (x_ik - x_jk)^2      (power-exp;
+//      emulator.c:173-209 with the constant exp(-2 theta_k) factored out, maxmultimin.c:530-538,583-602)
+// Matern (deviation D-3): one slot, (alpha_i alpha_j - Cinv_ij) * f(t), t = root * r / rho.
+// dC/dtheta is never stored.  grid (npad/64, npad/64, B) (upper tiles exit), 256 threads,
+// dynamic smem (2*d*64 + 2*64) doubles.
+template <int KERNEL>
+__global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ Cbase, long long strideC, int ld,
+                                                    const double *__restrict__ ABbase, long long strideAB, int ncp,
+                                                    const double *__restrict__ X, int n, int d,
+                                                    const double *__restrict__ consts, double *__restrict__ part, int ntiles64)
+{
+	const int bj = blockIdx.x, bi = blockIdx.y, b = blockIdx.z;
+	if (bj > bi) return;
+	extern __shared__ double sm[];
+	double *sXi = sm, *sXj = sm + d * CT;
+	double *sAi = sm + 2 * d * CT, *sAj = sAi + CT;
+	__shared__ double sc[CONST_STRIDE];
+	__shared__ double red[8][MAXD];
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const double *cg = consts + (size_t)b * CONST_STRIDE;
+	for (int i = tid; i < 4 + 3 * d; i += 256) sc[i] = cg[i];
+	const int i0 = bi * CT, j0 = bj * CT;
+	for (int idx = tid; idx < CT * d; idx += 256) {
+		int r = idx / d, k = idx - r * d;
+		sXi[k * CT + r] = (i0 + r < n) ? X[(size_t)(i0 + r) * d + k] : 0.0;
+		sXj[k * CT + r] = (j0 + r < n) ? X[(size_t)(j0 + r) * d + k] : 0.0;
+	}
+	const double *AB = ABbase + b * strideAB;
+	if (tid < CT) sAi[tid] = AB[(size_t)(i0 + tid) * ncp];
+	else if (tid < 2 * CT) sAj[tid - CT] = AB[(size_t)(j0 + tid - CT) * ncp];
+	__syncthreads();
+	const int tx = tid & 15, ty = tid >> 4;
+	const double *C = Cbase + b * strideC;
+	double w[4][4];
+#pragma unroll
+	for (int r = 0; r < 4; r++) {
+		const int li = ty + 16 * r, gi = i0 + li;
+#pragma unroll
+		for (int c = 0; c < 4; c++) {
+			const int lj = tx + 16 * c, gj = j0 + lj;
+			double v = 0.0;
+			if (gi > gj && gi < n) v = sAi[li] * sAj[lj] - C[(size_t)gi * ld + gj];
+			w[r][c] = v;
+		}
+	}
+	const int nslots = (KERNEL == 1) ? d : 1;
+	if (KERNEL == 1) {
+		for (int k = 0; k < d; k++) {
+			const double ak = sc[4 + d + k];
+			double s = 0.0;
+#pragma unroll
+			for (int r = 0; r < 4; r++) {
+				const double xi = sXi[k * CT + ty + 16 * r];
+#pragma unroll
+				for (int c = 0; c < 4; c++) {
+					const double dl = xi - sXj[k * CT + tx + 16 * c];
+					const double q = dl * dl;
+					s += w[r][c] * (q * exp(-ak * q));
+				}
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+			if (lane == 0) red[warp][k] = s;
+		}
+	} else {
+		const double root = (KERNEL == 2) ? 1.732050808 : 2.236067978;
+		const double rho = sc[2];
+		double s = 0.0;
+#pragma unroll
+		for (int r = 0; r < 4; r++)
+#pragma unroll
+			for (int c = 0; c < 4; c++) {
+				double r2 = 0.0;
+				for (int k = 0; k < d; k++) {
+					const double dl = sXi[k * CT + ty + 16 * r] - sXj[k * CT + tx + 16 * c];
+					r2 += dl * dl;
+				}
+				const double t = root * (sqrt(r2) / rho);
+				const double f = (KERNEL == 2) ? t * t * exp(-t) : (t * t / 3.0) * (1.0 + t) * exp(-t);
+				s += w[r][c] * f;
+			}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+		if (lane == 0) red[warp][0] = s;
+	}
+	__syncthreads();
+	if (tid < nslots) {
+		double s = 0.0;
+#pragma unroll
+		for (int wv = 0; wv < 8; wv++) s += red[wv][tid];
+		// lower-triangular tile index
+		const size_t tile = (size_t)bi * (bi + 1) / 2 + bj;
+		const size_t ntl = (size_t)ntiles64 * (ntiles64 + 1) / 2;
+		part[((size_t)b * ntl + tile) * MAXD + tid] = s;
+	}
+}
+
+// final gradient assembly, one CTA per point (maxmultimin.c:514-538):
+//  g_nugget = -( -0.5 nug tr(Cinv) + 0.5 nug alpha.alpha )
+//  g_len_k  = -sigma2 * exp(-2 theta_k) * sum_{i>j} (...)      (the i<j half is the mirror image)
+__global__ void __launch_bounds__(256) k_grad_final(const double *__restrict__ part, int ntiles64, const double *__restrict__ Cbase,
+                                                    long long strideC, int ld, const double *__restrict__ ABbase, long long strideAB,
+                                                    int ncp, int n, int d, int kernel, const double *__restrict__ consts,
+                                                    double *__restrict__ res)
+{
+	__shared__ double scratch[8];
+	const int b = blockIdx.x, tid = threadIdx.x;
+	const double *C = Cbase + b * strideC;
+	const double *AB = ABbase + b * strideAB;
+	const double *cg = consts + (size_t)b * CONST_STRIDE;
+	double *r = res + (size_t)b * RES_STRIDE;
+	double tr = 0.0, aa = 0.0;
+	for (int i = tid; i < n; i += 256) {
+		tr += C[(size_t)i * ld + i];
+		double a = AB[(size_t)i * ncp];
+		aa += a * a;
+	}
+	tr = block_sum_256(tr, scratch);
+	aa = block_sum_256(aa, scratch);
+	const size_t ntl = (size_t)ntiles64 * (ntiles64 + 1) / 2;
+	const int nslots = (kernel == 1) ? d : 1;
+	const bool failed = r[2] != 0.0;
+	const double sigma2 = cg[3];
+	const double amp = exp(log(sigma2));  // maxmultimin.c:514
+	for (int k = 0; k < nslots; k++) {
+		double s = 0.0;
+		for (size_t tix = tid; tix < ntl; tix += 256) s += part[((size_t)b * ntl + tix) * MAXD + k];
+		s = block_sum_256(s, scratch);
+		if (tid == 0) {
+			const double e2 = (kernel == 1) ? cg[4 + 2 * d + k] : 1.0;
+			r[RES_GRAD + 1 + k] = failed ? nan("") : -1.0 * (amp * e2 * s);
+		}
+	}
+	if (tid == 0) {
+		const double nug = cg[1];
+		r[6] = tr;
+		r[7] = aa;
+		r[RES_GRAD] = failed ? nan("") : -1.0 * (-0.5 * nug * tr + 0.5 * nug * aa);
+	}
+}
+
+// pack results for the device-pointer API: out[b] = (negL, sigma2, status, logdet, grad[nth1])
+__global__ void k_pack_results(const double *__restrict__ res, int B, int nth1, double *__restrict__ out)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= B) return;
+	const double *r = res + (size_t)b * RES_STRIDE;
+	double *o = out + (size_t)b * (nth1 + 4);
+	o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+	for (int k = 0; k < nth1; k++) o[4 + k] = r[RES_GRAD + k];
+}
+
+// ---- prediction epilogue (emulator.c:672-704, :720-785; emulator_struct.c:124-143) ---------------------
+//  mean = h.beta + k.a               a = C^-1 (y - H beta)
+//  var  = kappa - |L^-1 k|^2 + rho^T Minv rho,   rho = h - (C^-1 H)^T k
+// KA[q][0] = k.a, KA[q][1+c] = ((C^-1 H)^T k)_c ;  vsq_part[blk][q] = partial |W k|^2
+__global__ void __launch_bounds__(128) k_pred_final(const double *__restrict__ Q, int mq, int d, int order, int p,
+                                                    const double *__restrict__ KA, int ncp, const double *__restrict__ vsq_part,
+                                                    int nblk, int ldq, const double *__restrict__ beta,
+                                                    const double *__restrict__ Minv, double kappa,
+                                                    double *__restrict__ mean, double *__restrict__ var)
+{
+	__shared__ double sM[MAXNCP * MAXNCP];
+	__shared__ double sb[MAXNCP];
+	for (int i = threadIdx.x; i < p * p; i += blockDim.x) sM[i] = Minv[(i / p) * MAXNCP + (i % p)];
+	for (int i = threadIdx.x; i < p; i += blockDim.x) sb[i] = beta[i];
+	__syncthreads();
+	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= mq) return;
+	const double *x = Q + (size_t)q * d;
+	const double *ka = KA + (size_t)q * ncp;
+	double rho[MAXNCP];
+	double hb = 0.0;
+	for (int c = 0; c < p; c++) {
+		double h;
+		if (c == 0) h = 1.0;
+		else {
+			int k = (c - 1) % d, pw = (c - 1) / d;
+			double xv = x[k];
+			h = (pw == 0) ? xv : (pw == 1 ? xv * xv : xv * xv * xv);
+		}
+		hb += h * sb[c];
+		rho[c] = h - ka[1 + c];
+	}
+	double reg = 0.0;
+	for (int i = 0; i < p; i++) {
+		double s = 0.0;
+		for (int c = 0; c < p; c++) s += sM[i * p + c] * rho[c];
+		reg += rho[i] * s;
+	}
+	double vs = 0.0;
+	for (int k = 0; k < nblk; k++) vs += vsq_part[(size_t)k * ldq + q];
+	mean[q] = hb + ka[0];
+	var[q] = kappa - vs + reg;
+}
+
+}  // namespace emub

@@ -1,0 +1,282 @@
+"""ctypes binding of the C-ABI in include/emu_b200.h (madaiemulator_b200/csrc/libemub.so).
+
+This is the host-side mirror of the reference's libEmu operator interface for the hot path
+(evalFnMulti / gradFnMulti / makeCovMatrix / alloc_emulator_struct / emulate_point, see the header for
+file:line citations).  There is no CPU fallback: if the CUDA library is missing or no B200 is visible
+every call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libemub.so")
+
+POWEREXP, MATERN32, MATERN52 = 1, 2, 3
+OK, EDOM, EREG, EINVAL, ECUDA, ENOMEM = 0, 1, 2, 3, 4, 5
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+_vp = ctypes.c_void_p
+_ci = ctypes.c_int
+_ll = ctypes.c_longlong
+
+FAMILIES = ["cov", "potf2", "gemm_chol", "gemm_trtri", "gemm_lauum", "skinny", "small", "grad", "kcross",
+            "gemm_pred", "pred_final"]
+
+# every symbol include/emu_b200.h declares (checked by tests/test_cabi_symbols.py)
+SYMBOLS = [
+    "emub_ctx_create", "emub_ctx_destroy", "emub_last_error", "emub_version", "emub_ctx_stream",
+    "emub_ctx_set_groups", "emub_model_create", "emub_model_destroy", "emub_model_nthetas",
+    "emub_model_nregression_fns", "emub_model_slots", "emub_model_set_training", "emub_cov_matrix",
+    "emub_h_matrix", "emub_k_vectors", "emub_loglik_grad_batch", "emub_loglik_grad_batch_dev",
+    "emub_ctx_synchronize", "emub_loglik_extras", "emub_emulator_create", "emub_emulator_destroy",
+    "emub_emulator_beta", "emub_predict_batch", "emub_predict_batch_dev", "emub_profile_enable",
+    "emub_profile_reset", "emub_profile_read", "emub_profile_name", "emub_launch_count", "emub_debug_fetch",
+    "emub_debug_cholesky",
+]
+
+
+class EmubError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("emub error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libemub.so (raises if it has not been built: there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("CUDA engine %s is missing: run `make -C madaiemulator_b200/csrc` "
+                           "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    L.emub_last_error.restype = ctypes.c_char_p
+    L.emub_version.restype = ctypes.c_char_p
+    L.emub_profile_name.restype = ctypes.c_char_p
+    L.emub_profile_name.argtypes = [_ci]
+    L.emub_ctx_create.argtypes = [_ci, ctypes.POINTER(_vp)]
+    L.emub_ctx_destroy.argtypes = [_vp]
+    L.emub_ctx_destroy.restype = None
+    L.emub_ctx_stream.argtypes = [_vp]
+    L.emub_ctx_stream.restype = _vp
+    L.emub_ctx_set_groups.argtypes = [_vp, _ci]
+    L.emub_ctx_synchronize.argtypes = [_vp]
+    L.emub_model_create.argtypes = [_vp, _dp, _ci, _ci, _ci, _dp, _ci, _ci, _ci, ctypes.POINTER(_vp)]
+    L.emub_model_destroy.argtypes = [_vp]
+    L.emub_model_destroy.restype = None
+    L.emub_model_nthetas.argtypes = [_vp]
+    L.emub_model_nregression_fns.argtypes = [_vp]
+    L.emub_model_slots.argtypes = [_vp]
+    L.emub_model_set_training.argtypes = [_vp, _dp]
+    L.emub_cov_matrix.argtypes = [_vp, _dp, _dp, _ci]
+    L.emub_h_matrix.argtypes = [_vp, _dp, _ci]
+    L.emub_k_vectors.argtypes = [_vp, _dp, _dp, _ci, _ci, _dp, _ci]
+    L.emub_loglik_grad_batch.argtypes = [_vp, _dp, _ci, _ci, _dp, _dp, _dp, _ip]
+    L.emub_loglik_grad_batch_dev.argtypes = [_vp, _vp, _ci, _ci, _vp]
+    L.emub_loglik_extras.argtypes = [_vp, _ci, _dp, _dp]
+    L.emub_emulator_create.argtypes = [_vp, _dp, ctypes.POINTER(_vp)]
+    L.emub_emulator_destroy.argtypes = [_vp]
+    L.emub_emulator_destroy.restype = None
+    L.emub_emulator_beta.argtypes = [_vp, _dp]
+    L.emub_predict_batch.argtypes = [_vp, _dp, _ci, _ci, _dp, _dp]
+    L.emub_predict_batch_dev.argtypes = [_vp, _vp, _ci, _vp, _vp]
+    L.emub_profile_enable.argtypes = [_vp, _ci]
+    L.emub_profile_reset.argtypes = [_vp]
+    L.emub_profile_read.argtypes = [_vp, _ci, _dp, ctypes.POINTER(_ll), _dp]
+    L.emub_launch_count.argtypes = [_vp]
+    L.emub_launch_count.restype = _ll
+    L.emub_debug_fetch.argtypes = [_vp, _ci, _ci, _dp, _ci]
+    L.emub_debug_cholesky.argtypes = [_vp, _dp, _dp, _ci, _dp]
+    _lib = L
+    return L
+
+
+def _P(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _check(rc):
+    if rc != OK:
+        raise EmubError(rc, lib().emub_last_error().decode())
+
+
+class Context:
+    """One GPU (emub_ctx)."""
+
+    def __init__(self, device=0, groups=None):
+        self.L = lib()
+        h = _vp()
+        _check(self.L.emub_ctx_create(device, ctypes.byref(h)))
+        self.h = h
+        self.device = device
+        if groups is not None:
+            self.set_groups(groups)
+
+    def set_groups(self, g):
+        _check(self.L.emub_ctx_set_groups(self.h, g))
+
+    def stream(self):
+        return self.L.emub_ctx_stream(self.h)
+
+    def synchronize(self):
+        _check(self.L.emub_ctx_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.L.emub_launch_count(self.h))
+
+    def profile(self, on):
+        _check(self.L.emub_profile_enable(self.h, 1 if on else 0))
+        _check(self.L.emub_profile_reset(self.h))
+
+    def profile_read(self):
+        out = {}
+        for i, name in enumerate(FAMILIES):
+            ms, n, w = ctypes.c_double(), _ll(), ctypes.c_double()
+            _check(self.L.emub_profile_read(self.h, i, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(w)))
+            out[name] = dict(ms=ms.value, launches=n.value, work=w.value)
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.emub_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Model:
+    """Design + training vector + kernel + regression order on the device (emub_model)."""
+
+    def __init__(self, ctx, X, y, kernel=POWEREXP, order=0, max_slots=0):
+        self.ctx = ctx
+        self.L = ctx.L
+        self.X = _c(X)
+        self.y = _c(y)
+        self.n, self.d = self.X.shape
+        h = _vp()
+        _check(self.L.emub_model_create(ctx.h, _P(self.X), self.d, self.n, self.d, _P(self.y), kernel, order,
+                                        max_slots, ctypes.byref(h)))
+        self.h = h
+        self.kernel, self.order = kernel, order
+        self.nthetas = self.L.emub_model_nthetas(h)
+        self.p = self.L.emub_model_nregression_fns(h)
+        self.slots = self.L.emub_model_slots(h)
+
+    def set_training(self, y):
+        self.y = _c(y)
+        _check(self.L.emub_model_set_training(self.h, _P(self.y)))
+
+    def cov_matrix(self, thetas):
+        C = np.empty((self.n, self.n))
+        _check(self.L.emub_cov_matrix(self.h, _P(_c(thetas)), _P(C), self.n))
+        return C
+
+    def h_matrix(self):
+        H = np.empty((self.n, self.p))
+        _check(self.L.emub_h_matrix(self.h, _P(H), self.p))
+        return H
+
+    def k_vectors(self, thetas, pts):
+        pts = _c(pts).reshape(-1, self.d)
+        K = np.empty((self.n, pts.shape[0]))
+        _check(self.L.emub_k_vectors(self.h, _P(_c(thetas)), _P(pts), self.d, pts.shape[0], _P(K), pts.shape[0]))
+        return K
+
+    def loglik_grad_batch(self, thetas, want_grad=True):
+        """thetas: B x (nthetas-1).  Returns dict(negL[B], grad[B, nthetas-1], sigma2[B], status[B])."""
+        th = _c(thetas).reshape(-1, self.nthetas - 1)
+        B = th.shape[0]
+        negL, s2 = np.empty(B), np.empty(B)
+        grad = np.zeros((B, self.nthetas - 1))
+        st = np.zeros(B, dtype=np.int32)
+        _check(self.L.emub_loglik_grad_batch(self.h, _P(th), B, 1 if want_grad else 0, _P(negL), _P(grad), _P(s2),
+                                             st.ctypes.data_as(_ip)))
+        return dict(negL=negL, grad=grad, sigma2=s2, status=st)
+
+    def loglik_grad(self, theta_less_amp, want_grad=True):
+        r = self.loglik_grad_batch(np.asarray(theta_less_amp)[None, :], want_grad)
+        ld, beta = ctypes.c_double(), np.zeros(self.p)
+        _check(self.L.emub_loglik_extras(self.h, 0, ctypes.byref(ld), _P(beta)))
+        return dict(status=int(r["status"][0]), negL=float(r["negL"][0]), grad=r["grad"][0], sigma2=float(r["sigma2"][0]),
+                    logdet=ld.value, beta=beta)
+
+    def loglik_grad_batch_dev(self, d_thetas_ptr, B, want_grad, d_out_ptr):
+        _check(self.L.emub_loglik_grad_batch_dev(self.h, d_thetas_ptr, B, 1 if want_grad else 0, d_out_ptr))
+
+    def debug_fetch(self, slot, which):
+        out = np.empty((self.n, self.n))
+        _check(self.L.emub_debug_fetch(self.h, slot, which, _P(out), self.n))
+        return out
+
+    def debug_cholesky(self, theta_less_amp):
+        Lm = np.zeros((self.n, self.n))
+        ld = ctypes.c_double()
+        rc = self.L.emub_debug_cholesky(self.h, _P(_c(theta_less_amp)), _P(Lm), self.n, ctypes.byref(ld))
+        if rc not in (OK, EDOM):
+            _check(rc)
+        return rc, Lm, ld.value
+
+    def emulator(self, thetas):
+        return Emulator(self, thetas)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.emub_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Emulator:
+    """Cached factor for prediction (emub_emulator; the reference's emulator_struct)."""
+
+    def __init__(self, model, thetas):
+        self.model = model
+        self.L = model.L
+        h = _vp()
+        _check(self.L.emub_emulator_create(model.h, _P(_c(thetas)), ctypes.byref(h)))
+        self.h = h
+
+    def emulate(self, pts):
+        pts = _c(pts).reshape(-1, self.model.d)
+        m = pts.shape[0]
+        mean, var = np.empty(m), np.empty(m)
+        _check(self.L.emub_predict_batch(self.h, _P(pts), self.model.d, m, _P(mean), _P(var)))
+        return mean, var
+
+    def emulate_dev(self, d_pts_ptr, m, d_mean_ptr, d_var_ptr):
+        _check(self.L.emub_predict_batch_dev(self.h, d_pts_ptr, m, d_mean_ptr, d_var_ptr))
+
+    def beta(self):
+        b = np.empty(self.model.p)
+        _check(self.L.emub_emulator_beta(self.h, _P(b)))
+        return b
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.emub_emulator_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,226 @@
+"""GPU parity tests: the CUDA engine (through the C-ABI, madaiemulator_b200.engine) against the CPU oracle
+(oracle/emu_oracle.c) and the committed golden fixtures that the reference's own sources produced.
+
+Tolerances (north_star: 1e-9 relative in FP64):
+  * covariance entries, -L, sigma2, beta, emulated mean: 1e-9 relative (a floor on the denominator where the
+    quantity can pass through zero);
+  * gradient components: 1e-9 relative to the magnitude of their constituent terms (|trace term| + |quadratic
+    term|, SURVEY hard part 3) -- in practice relative to max(|g|, 1e-3 * max|g|);
+  * emulated variance: |dv| <= 1e-9 * kappa (it is a cancellation kappa - k^T C^-1 k).
+"""
+import numpy as np
+import pytest
+
+from madaiemulator_b200 import datasets as ds
+from tests.helpers import golden_names, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from madaiemulator_b200 import engine
+    c = engine.Context(0)
+    yield c
+    c.close()
+
+
+def _oracle(X, y, kernel, order):
+    from oracle.pyoracle import PortOracle
+    return PortOracle(X, y, kernel, order)
+
+
+def _grad_err(g, gref):
+    scale = np.maximum(np.abs(gref), 1e-3 * np.max(np.abs(gref)) + 1e-300)
+    return float(np.max(np.abs(g - gref) / scale))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fixture(ctx, name):
+    from madaiemulator_b200 import engine
+    c = load_golden(name)
+    m = engine.Model(ctx, c["X"], c["y"], c["kernel"], c["order"], max_slots=4)
+    n = c["n"]
+    C = m.cov_matrix(c["theta_full"])
+    rows = c["cov_rows"]
+    assert relerr(C[rows], c["cov_row_values"].reshape(len(rows), -1), 1e-300) < TOL
+    assert relerr(np.diag(C), c["cov_diag"]) < TOL
+    assert np.array_equal(C, C.T)
+    assert np.array_equal(m.h_matrix().ravel(), c["H"].ravel())
+    e = m.emulator(c["theta_full"])
+    mean, var = e.emulate(c["pts"])
+    assert relerr(mean, c["emu_mean"], 1e-3) < TOL
+    assert np.max(np.abs(var - c["emu_var"])) < TOL * max(1.0, float(c["kappa"]))
+    assert relerr(e.beta(), c["emu_beta"], 1e-6) < TOL
+    e.close()
+    if c["kernel"] == 1:
+        r = m.loglik_grad(c["theta_less_amp"])
+        assert r["status"] == 0
+        assert relerr(r["negL"], c["negL_logsum"]) < TOL
+        assert relerr(r["logdet"], c["logdet"]) < TOL
+        assert relerr(r["sigma2"], c["sigma2"]) < TOL
+        assert relerr(r["beta"], c["beta"], 1e-6) < TOL
+        assert _grad_err(r["grad"], c["grad"]) < TOL
+        if np.isfinite(c["negL_literal"]):
+            # deviation D-1: identical to the reference's literal product determinant where that is finite
+            assert relerr(r["negL"], c["negL_literal"]) < TOL
+    m.close()
+
+
+@pytest.mark.parametrize("n,d,order,kernel", [(40, 1, 0, 1), (129, 3, 1, 1), (300, 6, 2, 1), (520, 10, 3, 1), (700, 15, 1, 1),
+                                              (200, 4, 1, 2), (260, 6, 2, 3)])
+def test_synthetic_vs_oracle(ctx, n, d, order, kernel):
+    from madaiemulator_b200 import engine
+    X = ds.synthetic_design(n, d, seed=ds.SEED + n)
+    y = ds.synthetic_response(X, seed=ds.SEED + n)
+    o = _oracle(X, y, kernel, order)
+    m = engine.Model(ctx, X, y, kernel, order, max_slots=4)
+    rng = np.random.default_rng(n)
+    B = 5
+    if kernel == 1:
+        ths = np.stack([np.concatenate([[rng.uniform(-5, -2)], rng.uniform(0.0, 1.5, d)]) for _ in range(B)])
+    else:
+        ths = np.stack([np.array([rng.uniform(-5, -2), rng.uniform(0.0, 1.5)]) for _ in range(B)])
+    r = m.loglik_grad_batch(ths)
+    for b in range(B):
+        ref = o.loglik_grad(ths[b])
+        assert r["status"][b] == ref["status"] == 0
+        assert relerr(r["negL"][b], ref["negL"]) < TOL
+        assert relerr(r["sigma2"][b], ref["sigma2"]) < TOL
+        assert _grad_err(r["grad"][b], ref["grad"]) < TOL
+    # value-only path returns the same value
+    r2 = m.loglik_grad_batch(ths, want_grad=False)
+    assert np.array_equal(r2["negL"], r["negL"])
+    # prediction
+    if kernel == 1:
+        full = np.concatenate([[rng.uniform(-1, 1)], ths[0]])
+    else:
+        full = np.array([1.7, 0.05, 0.4])
+    pts = ds.synthetic_queries(300, d, seed=n)
+    pts[0] = X[n // 2]  # coincidence with a design point: nugget in k and kappa (emulator.c:136-150)
+    pts[1] = X[0]
+    m1, v1 = o.emulator(full).emulate(pts)
+    e = m.emulator(full)
+    m2, v2 = e.emulate(pts)
+    kappa = o.cov_pair(pts[5], pts[5], full)
+    assert relerr(m2, m1, 1e-3) < TOL
+    assert np.max(np.abs(v2 - v1)) < TOL * max(1.0, kappa)
+    assert relerr(m.cov_matrix(full), o.cov_matrix(full), 1e-300) < TOL
+    K = m.k_vectors(full, pts[:7])
+    Kref = np.stack([np.array([o.cov_pair(X[i], pts[q], full) for i in range(n)]) for q in range(7)], axis=1)
+    Kref[Kref < 1e-10] = 0.0
+    assert relerr(K, Kref, 1e-300) < TOL
+    e.close()
+    m.close()
+
+
+def test_factor_internals(ctx):
+    """Cholesky factor, triangular inverse and explicit inverse against numpy (float64 LAPACK)."""
+    from madaiemulator_b200 import engine
+    n, d = 700, 5
+    X = ds.synthetic_design(n, d)
+    y = ds.synthetic_response(X)
+    m = engine.Model(ctx, X, y, 1, 0, max_slots=2)
+    th = ds.default_theta_less_amp(d)
+    C = _oracle(X, y, 1, 0).cov_matrix(np.concatenate([[0.0], th]))
+    rc, L, logdet = m.debug_cholesky(th)
+    assert rc == 0
+    Lref = np.linalg.cholesky(C)
+    assert np.max(np.abs(L - Lref)) < 1e-11
+    assert abs(logdet - 2 * np.sum(np.log(np.diag(Lref)))) < 1e-9 * abs(logdet)
+    r = m.loglik_grad_batch(th[None, :])
+    assert r["status"][0] == 0
+    W = np.tril(m.debug_fetch(0, 1))
+    Wref = np.linalg.inv(Lref)
+    assert np.max(np.abs(W - Wref)) < 1e-9 * np.max(np.abs(Wref))
+    Cinv = np.tril(m.debug_fetch(0, 0))
+    Cinv_ref = np.tril(np.linalg.inv(C))
+    assert np.max(np.abs(Cinv - Cinv_ref)) < 1e-9 * np.max(np.abs(Cinv_ref))
+    m.close()
+
+
+def test_not_positive_definite_reports_edom(ctx):
+    """evalFnMulti returns NaN when the Cholesky fails (maxmultimin.c:327-350); the engine flags the
+    point and carries on with the rest of the batch."""
+    from madaiemulator_b200 import engine
+    X = np.array([[0.0], [1e-12], [1.0], [2.0]])  # two numerically identical points
+    y = np.array([1.0, 1.1, 0.3, 0.2])
+    m = engine.Model(ctx, X, y, 1, 0, max_slots=2)
+    ths = np.array([[-800.0, 0.0], [-3.0, 0.0]])  # nugget exp(-800) = 0 -> singular; second point fine
+    r = m.loglik_grad_batch(ths)
+    assert r["status"][0] == engine.EDOM and np.isnan(r["negL"][0]) and np.all(np.isnan(r["grad"][0]))
+    assert r["status"][1] == 0 and np.isfinite(r["negL"][1])
+    ref = _oracle(X, y, 1, 0).loglik_grad(ths[1])
+    assert relerr(r["negL"][1], ref["negL"]) < TOL
+    m.close()
+
+
+def test_batch_larger_than_slots_and_groups(ctx):
+    from madaiemulator_b200 import engine
+    n, d = 300, 4
+    X = ds.synthetic_design(n, d)
+    y = ds.synthetic_response(X)
+    m = engine.Model(ctx, X, y, 1, 1, max_slots=3)
+    rng = np.random.default_rng(3)
+    ths = np.stack([np.concatenate([[rng.uniform(-5, -2)], rng.uniform(0.0, 1.5, d)]) for _ in range(11)])
+    ctx.set_groups(1)
+    a = m.loglik_grad_batch(ths)
+    ctx.set_groups(3)
+    b = m.loglik_grad_batch(ths)
+    ctx.set_groups(2)
+    # lock-step batching and stream groups must not change a single bit
+    assert np.array_equal(a["negL"], b["negL"]) and np.array_equal(a["grad"], b["grad"])
+    o = _oracle(X, y, 1, 1)
+    for i in (0, 5, 10):
+        ref = o.loglik_grad(ths[i])
+        assert relerr(a["negL"][i], ref["negL"]) < TOL
+        assert _grad_err(a["grad"][i], ref["grad"]) < TOL
+    m.close()
+
+
+def test_large_properties(ctx):
+    """BASELINE size n=4096, d=10: size-independent properties (the oracle would take minutes here):
+    W L = I on sampled rows, Cinv C = I on sampled rows, gradient of a smooth surrogate by symmetry, and
+    prediction at design points reproduces the training data up to the nugget."""
+    from madaiemulator_b200 import engine
+    n, d = 4096, 10
+    X = ds.synthetic_design(n, d)
+    y = ds.synthetic_response(X)
+    m = engine.Model(ctx, X, y, 1, 0, max_slots=2)
+    th = ds.default_theta_less_amp(d)
+    rc, L, logdet = m.debug_cholesky(th)
+    assert rc == 0
+    r = m.loglik_grad_batch(th[None, :])
+    assert r["status"][0] == 0 and np.isfinite(r["negL"][0])
+    W = np.tril(m.debug_fetch(0, 1))
+    Cinv = np.tril(m.debug_fetch(0, 0))
+    Cinv = Cinv + np.tril(Cinv, -1).T
+    rows = np.array([0, 1, 127, 128, 1000, 2047, 2048, 4000, 4095])
+    WL = W[rows] @ L
+    E = np.zeros_like(WL)
+    E[np.arange(len(rows)), rows] = 1.0
+    assert np.max(np.abs(WL - E)) < 1e-10
+    C = m.cov_matrix(np.concatenate([[0.0], th]))
+    CC = Cinv[rows] @ C
+    assert np.max(np.abs(CC - E)) < 1e-8
+    # log-det against numpy on the same matrix
+    sign, ld = np.linalg.slogdet(C)
+    assert sign > 0 and abs(ld - logdet) < 1e-9 * abs(ld)
+    # likelihood value against a float64 numpy evaluation of the same formulas (Appendix A)
+    H = np.ones((n, 1))
+    a = Cinv @ y
+    b = Cinv @ H
+    beta = (H.T @ a) / (H.T @ b)
+    res = y - H[:, 0] * beta[0, 0] if beta.ndim == 2 else y - H[:, 0] * beta[0]
+    negL = 0.5 * logdet + (n / 2.0) * 1.83788 + 0.5 * res @ (Cinv @ res)
+    assert relerr(r["negL"][0], negL) < 1e-9
+    # prediction at design points: mean = y - nugget-sized correction, variance ~ O(nugget)
+    full = np.concatenate([[np.log(r["sigma2"][0])], th])
+    e = m.emulator(full)
+    mean, var = e.emulate(X[:256])
+    assert np.max(np.abs(mean - y[:256])) < 0.2
+    assert np.all(var > -1e-9) and np.all(var < 0.1 * np.exp(full[0]) + 1e-6)
+    e.close()
+    m.close()
