@@ -5,15 +5,15 @@
 //   X   (npad x d)            design, padded rows zero
 //   Yh  (npad x ncp)          [ y | H | 0 ]  (ncp = p + 1 rounded up to 8)
 //   per slot (one in-flight likelihood evaluation):
-//     bufA (npad x npad)      C -> L (in place, lower) -> Cinv = W^T W (lower tiles)
+//     bufA (npad x npad)      C (lower) -> scratch T = L21 W11 of the inverse merge -> Cinv = W^T W (lower tiles)
+//     bufT (npad x npad)      L (lower)
 //     bufW (npad x npad)      W = L^-1 (lower; diagonal blocks from POTF2, the rest by recursive merge)
-//     bufT (npad x npad)      merge temporary  T = L21 W11
 //     UG (npad x ncp)         W [y | H]      AB (npad x ncp)  W^T UG = [alpha | C^-1 H]
 //     small per-slot arrays (constants, log-det partials, Gram partials, gradient partials, results)
 //
 // One likelihood + gradient evaluation (reference: evalFnGradMulti, maxmultimin.c:615) is
-//   K1 covariance (lower) -> blocked right-looking Cholesky (POTF2 on the diagonal block, DMMA
-//   TRSM-as-GEMM panel, DMMA SYRK trailing update) -> recursive triangular inverse (DMMA) ->
+//   K1 covariance (lower) -> recursive Cholesky + triangular inverse (register-resident POTF2 on the 128 x 128
+//   diagonal blocks; DMMA TRSM-as-GEMM, SYRK and inverse-merge products with K = half the node size) ->
 //   skinny products + p x p regression algebra -> DMMA W^T W -> fused gradient reduction.
 // Slots are processed in lock step per stream group, groups run concurrently on their own streams.
 #include <cuda_runtime.h>
@@ -80,7 +80,9 @@ struct LaunchScope {
 	}
 };
 
-struct TrtriLevel { int t1_off, t1_cnt, t2_off, t2_cnt; double flops1, flops2; };
+// one kernel launch of the factorisation sequence (depth-first order of the recursion)
+enum { STEP_POTF2 = 0, STEP_TRSM, STEP_SYRK, STEP_TMUL, STEP_WMUL };
+struct FactorStep { int type; int off, cnt; int kblk; double flops; };
 
 struct emub_model {
 	emub_ctx *ctx;
@@ -88,8 +90,7 @@ struct emub_model {
 	size_t mat;  // npad * npad
 	double *dX, *dy, *dYh;
 	GemmTask *dTasks;
-	std::vector<int> trsm_off, trsm_cnt, syrk_off, syrk_cnt;
-	std::vector<TrtriLevel> levels;
+	std::vector<FactorStep> steps;
 	int lauum_off, lauum_cnt;
 	double lauum_flops;
 	double *bufA, *bufW, *bufT;
@@ -182,46 +183,60 @@ extern "C" int emub_profile_read(emub_ctx *c, int f, double *ms, long long *laun
 extern "C" long long emub_launch_count(emub_ctx *c) { return c ? c->launches : 0; }
 
 // ---- schedules --------------------------------------------------------------------------------------
+// Recursive factorisation of the block range [lo, hi):  A = L L^T and W = L^-1 together.
+//   rec(lo, mid);                                   L11 (bufT), W11 (bufW)
+//   L21 = A21 W11^T                                 TRSM as a GEMM against the inverse; bufA -> bufT
+//   A22 -= L21 L21^T                                SYRK, in place in bufA
+//   rec(mid, hi);                                   L22, W22
+//   T = L21 W11 ;  W21 = -W22 T                     triangular-inverse merge; T lives in the dead A21 region
+// Every GEMM therefore runs with K = the size of the half it multiplies against (94% of the flops at
+// K >= 1024 for n = 4096), instead of the K = 128 rank updates of a panel-by-panel sweep.
+static void build_factor(emub_model *m, int lo, int hi, std::vector<GemmTask> &tasks)
+{
+	const long long ld = m->npad;
+	auto off = [&](int bi, int bj) { return (long long)bi * TB * ld + (long long)bj * TB; };
+	auto by_k = [](const GemmTask &a, const GemmTask &b) { return a.klen > b.klen; };
+	auto emit = [&](int type, std::vector<GemmTask> &t) {
+		std::stable_sort(t.begin(), t.end(), by_k);
+		FactorStep st{type, (int)tasks.size(), (int)t.size(), 0, 0.0};
+		for (auto &x : t) { tasks.push_back(x); st.flops += 2.0 * TB * TB * (double)x.klen; }
+		m->steps.push_back(st);
+	};
+	if (hi - lo == 1) {
+		m->steps.push_back({STEP_POTF2, 0, 0, lo, 2.0 * TB * TB * TB / 3.0});
+		return;
+	}
+	const int mid = lo + (hi - lo + 1) / 2;
+	build_factor(m, lo, mid, tasks);
+	std::vector<GemmTask> t;
+	// L(i,j) = sum_{k in [lo, j]} A(i,k) W(j,k)^T          A = bufA KMAJOR, B = bufW KMAJOR -> bufT
+	for (int i = mid; i < hi; i++)
+		for (int j = lo; j < mid; j++) t.push_back({off(i, lo), off(j, lo), off(i, j), (j - lo + 1) * TB, 0});
+	emit(STEP_TRSM, t);
+	t.clear();
+	// A(i,j) -= sum_{k in [lo, mid)} L(i,k) L(j,k)^T      A, B = bufT KMAJOR -> bufA
+	for (int i = mid; i < hi; i++)
+		for (int j = mid; j <= i; j++) t.push_back({off(i, lo), off(j, lo), off(i, j), (mid - lo) * TB, 0});
+	emit(STEP_SYRK, t);
+	build_factor(m, mid, hi, tasks);
+	t.clear();
+	// T(i,j) = sum_{k in [j, mid)} L(i,k) W(k,j)           A = bufT KMAJOR, B = bufW RMAJOR -> bufA
+	for (int i = mid; i < hi; i++)
+		for (int j = lo; j < mid; j++) t.push_back({off(i, j), off(j, j), off(i, j), (mid - j) * TB, 0});
+	emit(STEP_TMUL, t);
+	t.clear();
+	// W(i,j) = - sum_{k in [mid, i]} W(i,k) T(k,j)         A = bufW KMAJOR, B = bufA RMAJOR -> bufW
+	for (int i = mid; i < hi; i++)
+		for (int j = lo; j < mid; j++) t.push_back({off(i, mid), off(mid, j), off(i, j), (i + 1 - mid) * TB, 0});
+	emit(STEP_WMUL, t);
+}
+
 static void build_schedules(emub_model *m, std::vector<GemmTask> &tasks)
 {
 	const long long ld = m->npad;
 	const int nb = m->nblk;
 	auto off = [&](int bi, int bj) { return (long long)bi * TB * ld + (long long)bj * TB; };
-	m->trsm_off.assign(nb, 0); m->trsm_cnt.assign(nb, 0); m->syrk_off.assign(nb, 0); m->syrk_cnt.assign(nb, 0);
-	for (int k = 0; k < nb; k++) {
-		m->trsm_off[k] = (int)tasks.size();
-		for (int i = k + 1; i < nb; i++) tasks.push_back({off(i, k), off(k, k), off(i, k), TB, 0});
-		m->trsm_cnt[k] = (int)tasks.size() - m->trsm_off[k];
-		m->syrk_off[k] = (int)tasks.size();
-		for (int i = k + 1; i < nb; i++)
-			for (int j = k + 1; j <= i; j++) tasks.push_back({off(i, k), off(j, k), off(i, j), TB, 0});
-		m->syrk_cnt[k] = (int)tasks.size() - m->syrk_off[k];
-	}
-	// recursive triangular inverse: level sb merges [c0, c0+sb) and [c0+sb, min(c0+2sb, nb))
-	for (int sb = 1; sb < nb; sb *= 2) {
-		TrtriLevel L{};
-		std::vector<GemmTask> t1, t2;
-		for (int c0 = 0; c0 < nb; c0 += 2 * sb) {
-			const int mid = c0 + sb;
-			if (mid >= nb) continue;
-			const int c1 = std::min(c0 + 2 * sb, nb);
-			for (int i = mid; i < c1; i++)
-				for (int j = c0; j < mid; j++) {
-					// T(i,j) = sum_{k in [j, mid)} L(i,k) W(k,j)       A = L KMAJOR, B = W RMAJOR
-					t1.push_back({off(i, j), off(j, j), off(i, j), (mid - j) * TB, 0});
-					// W(i,j) = - sum_{k in [mid, i]} W(i,k) T(k,j)     A = W KMAJOR, B = T RMAJOR
-					t2.push_back({off(i, mid), off(mid, j), off(i, j), (i + 1 - mid) * TB, 0});
-				}
-		}
-		auto by_k = [](const GemmTask &a, const GemmTask &b) { return a.klen > b.klen; };
-		std::stable_sort(t1.begin(), t1.end(), by_k);
-		std::stable_sort(t2.begin(), t2.end(), by_k);
-		L.t1_off = (int)tasks.size(); L.t1_cnt = (int)t1.size();
-		for (auto &t : t1) { tasks.push_back(t); L.flops1 += 2.0 * TB * TB * t.klen; }
-		L.t2_off = (int)tasks.size(); L.t2_cnt = (int)t2.size();
-		for (auto &t : t2) { tasks.push_back(t); L.flops2 += 2.0 * TB * TB * t.klen; }
-		m->levels.push_back(L);
-	}
+	build_factor(m, 0, nb, tasks);
 	// Cinv(i,j) = sum_{k >= i} W(k,i)^T W(k,j), i >= j     A = W RMAJOR, B = W RMAJOR
 	m->lauum_off = (int)tasks.size();
 	m->lauum_flops = 0;
@@ -374,37 +389,35 @@ static void launch_kcross(emub_model *m, cudaStream_t st, const double *consts, 
 	}
 }
 
-// Cholesky (in place in bufA, diagonal-block inverses into bufW) for `count` slots starting at s0
-static void run_cholesky(emub_model *m, cudaStream_t st, int s0, int count)
+// L (bufT) and W = L^-1 (bufW) from C (bufA) for `count` slots starting at s0
+static void run_factor(emub_model *m, cudaStream_t st, int s0, int count)
 {
 	emub_ctx *c = m->ctx;
 	const int ld = m->npad;
-	double *A = m->bufA + (size_t)s0 * m->mat, *W = m->bufW + (size_t)s0 * m->mat;
-	for (int k = 0; k < m->nblk; k++) {
-		{
-			LaunchScope ls(c, EMUB_K_POTF2, count * (2.0 * TB * TB * TB / 3.0), st);
-			k_potf2<<<count, POTF2_THREADS, POTF2_SMEM_BYTES, st>>>(A, (long long)m->mat, W, (long long)m->mat, ld, k, m->nblk,
-			                                                        m->dLogdet + (size_t)s0 * m->nblk, m->dInfo + s0);
-		}
-		// L(i,k) = A(i,k) Winv(k,k)^T
-		launch_gemm<KMAJOR, KMAJOR, EPI_STORE>(c, EMUB_K_GEMM_CHOL, 2.0 * TB * TB * TB * m->trsm_cnt[k], st, m->dTasks + m->trsm_off[k],
-		                                       m->trsm_cnt[k], count, A, m->mat, ld, W, m->mat, ld, A, m->mat, ld, 1.0);
-		// A(i,j) -= L(i,k) L(j,k)^T
-		launch_gemm<KMAJOR, KMAJOR, EPI_SUB>(c, EMUB_K_GEMM_CHOL, 2.0 * TB * TB * TB * m->syrk_cnt[k], st, m->dTasks + m->syrk_off[k],
-		                                     m->syrk_cnt[k], count, A, m->mat, ld, A, m->mat, ld, A, m->mat, ld, 1.0);
-	}
-}
-
-static void run_trtri(emub_model *m, cudaStream_t st, int s0, int count)
-{
-	emub_ctx *c = m->ctx;
-	const int ld = m->npad;
+	const long long ms = (long long)m->mat;
 	double *A = m->bufA + (size_t)s0 * m->mat, *W = m->bufW + (size_t)s0 * m->mat, *T = m->bufT + (size_t)s0 * m->mat;
-	for (const TrtriLevel &L : m->levels) {
-		launch_gemm<KMAJOR, RMAJOR, EPI_STORE>(c, EMUB_K_GEMM_TRTRI, L.flops1, st, m->dTasks + L.t1_off, L.t1_cnt, count, A, m->mat,
-		                                       ld, W, m->mat, ld, T, m->mat, ld, 1.0);
-		launch_gemm<KMAJOR, RMAJOR, EPI_STORE>(c, EMUB_K_GEMM_TRTRI, L.flops2, st, m->dTasks + L.t2_off, L.t2_cnt, count, W, m->mat,
-		                                       ld, T, m->mat, ld, W, m->mat, ld, -1.0);
+	for (const FactorStep &s : m->steps) {
+		const GemmTask *tk = m->dTasks + s.off;
+		switch (s.type) {
+		case STEP_POTF2: {
+			LaunchScope ls(c, EMUB_K_POTF2, count * s.flops, st);
+			k_potf2<<<count, POTF2_THREADS, POTF2_SMEM_BYTES, st>>>(A, ms, T, ms, W, ms, ld, s.kblk, m->nblk,
+			                                                        m->dLogdet + (size_t)s0 * m->nblk, m->dInfo + s0);
+			break;
+		}
+		case STEP_TRSM:
+			launch_gemm<KMAJOR, KMAJOR, EPI_STORE>(c, EMUB_K_GEMM_CHOL, s.flops, st, tk, s.cnt, count, A, ms, ld, W, ms, ld, T, ms, ld, 1.0);
+			break;
+		case STEP_SYRK:
+			launch_gemm<KMAJOR, KMAJOR, EPI_SUB>(c, EMUB_K_GEMM_CHOL, s.flops, st, tk, s.cnt, count, T, ms, ld, T, ms, ld, A, ms, ld, 1.0);
+			break;
+		case STEP_TMUL:
+			launch_gemm<KMAJOR, RMAJOR, EPI_STORE>(c, EMUB_K_GEMM_TRTRI, s.flops, st, tk, s.cnt, count, T, ms, ld, W, ms, ld, A, ms, ld, 1.0);
+			break;
+		case STEP_WMUL:
+			launch_gemm<KMAJOR, RMAJOR, EPI_STORE>(c, EMUB_K_GEMM_TRTRI, s.flops, st, tk, s.cnt, count, W, ms, ld, A, ms, ld, W, ms, ld, -1.0);
+			break;
+		}
 	}
 }
 
@@ -490,8 +503,7 @@ static void run_group(emub_model *m, cudaStream_t st, int s0, int count, int nth
 	}
 	cudaMemsetAsync(m->dInfo + s0, 0, sizeof(int) * count, st);
 	launch_cov(m, st, count, m->dConsts + (size_t)s0 * CONST_STRIDE, m->bufA + (size_t)s0 * m->mat, (long long)m->mat, 1);
-	run_cholesky(m, st, s0, count);
-	run_trtri(m, st, s0, count);
+	run_factor(m, st, s0, count);
 	run_regression(m, st, s0, count, emulator_mode);
 	if (want_grad) {
 		run_lauum(m, st, s0, count);
@@ -658,10 +670,10 @@ extern "C" int emub_debug_cholesky(emub_model *m, const double *theta_less_amp, 
 	}
 	CUDA_TRY(cudaMemsetAsync(m->dInfo, 0, sizeof(int), st));
 	launch_cov(m, st, 1, m->dConsts, m->bufA, (long long)m->mat, 1);
-	run_cholesky(m, st, 0, 1);
+	run_factor(m, st, 0, 1);
 	CUDA_TRY(cudaStreamSynchronize(st));
 	CUDA_TRY(cudaGetLastError());
-	CUDA_TRY(cudaMemcpy2D(L, sizeof(double) * ldl, m->bufA, sizeof(double) * m->npad, sizeof(double) * m->n, m->n, cudaMemcpyDeviceToHost));
+	CUDA_TRY(cudaMemcpy2D(L, sizeof(double) * ldl, m->bufT, sizeof(double) * m->npad, sizeof(double) * m->n, m->n, cudaMemcpyDeviceToHost));
 	std::vector<double> parts(m->nblk);
 	int info = 0;
 	CUDA_TRY(cudaMemcpy(parts.data(), m->dLogdet, sizeof(double) * m->nblk, cudaMemcpyDeviceToHost));

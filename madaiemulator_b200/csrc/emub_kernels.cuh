@@ -163,86 +163,159 @@ __global__ void k_set_y(const double *__restrict__ y, int n, int ncp, double *__
 	if (i < n) Yh[(size_t)i * ncp] = y[i];
 }
 
-// ---- POTF2: Cholesky of one 128 x 128 diagonal block + its triangular inverse, in shared memory ----
-// Right-looking column sweep.  The same row operations that reduce A to L are applied to the identity
-// (stored in the slots of the already eliminated columns), so after the sweep the lower triangle holds
-// L^-1; the finished columns of L are stashed transposed in the unused upper triangle.
-// grid (B), 256 threads, dynamic smem (128*129 + 3*128) doubles.
-constexpr int POTF2_THREADS = 256;
-constexpr int PS = TB + 1;
-constexpr int POTF2_SMEM_BYTES = (TB * PS + 3 * TB) * 8;
+// ---- POTF2: Cholesky of one 128 x 128 diagonal block + its triangular inverse, register resident ----
+// The block is cut into a 16 x 16 grid of 8 x 8 sub-blocks; the 136 lower ones live in the registers of
+// 136 threads (64 doubles each).  Right-looking column sweep with ONE barrier per column: the owners of
+// column j / row j publish their raw values to a double-buffered shared array, everybody derives the
+// pivot 1/a_jj itself and applies the rank-1 update  a(i,c) -= a(i,j) a(c,j) / a_jj  from registers.
+// The same row operations are applied to the identity, stored in the slots of the already eliminated
+// columns, so when the sweep ends the registers hold L^-1; finished columns of L go to a packed shared
+// array and are written out coalesced.
+// grid (B), POTF2_THREADS threads, dynamic smem POTF2_SMEM_BYTES.
+constexpr int POTF2_THREADS = 160;
+constexpr int POTF2_NBLOCKS = 136;
+constexpr int POTF2_LPACK = TB * (TB + 1) / 2;
+constexpr int POTF2_SMEM_BYTES = (POTF2_LPACK + 4 * TB) * 8;
 
-__global__ void __launch_bounds__(POTF2_THREADS) k_potf2(double *Abase, long long strideA, double *Wbase, long long strideW,
-                                                         int ld, int kblk, int nblk, double *__restrict__ logdet_parts,
-                                                         int *__restrict__ info)
+__global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, long long strideA, double *Lbase, long long strideL,
+                                                         double *Wbase, long long strideW, int ld, int kblk, int nblk,
+                                                         double *__restrict__ logdet_parts, int *__restrict__ info)
 {
 	extern __shared__ double sm[];
-	double *S = sm;
-	double *lcol = S + TB * PS;
-	double *vrow = lcol + TB;
-	double *ldiag = vrow + TB;
+	double *Lp = sm;                    // packed lower triangle of L: (i, c) at i (i + 1) / 2 + c
+	double *colbuf = sm + POTF2_LPACK;  // [2][128]
+	double *rowbuf = colbuf + 2 * TB;   // [2][128]
 	const int tid = threadIdx.x, b = blockIdx.x;
-	const int warp = tid >> 5, lane = tid & 31;
-	double *A = Abase + b * strideA + (size_t)kblk * TB * ld + (size_t)kblk * TB;
-	double *W = Wbase + b * strideW + (size_t)kblk * TB * ld + (size_t)kblk * TB;
-	for (int idx = tid; idx < TB * TB; idx += POTF2_THREADS) {
-		int i = idx >> 7, c = idx & 127;
-		S[i * PS + c] = (c <= i) ? A[(size_t)i * ld + c] : 0.0;
+	const size_t blk = (size_t)kblk * TB * ld + (size_t)kblk * TB;
+	const double *A = Abase + b * strideA + blk;
+	double *Lg = Lbase + b * strideL + blk;
+	double *Wg = Wbase + b * strideW + blk;
+	const bool active = tid < POTF2_NBLOCKS;
+	int bi = 0, bj = 0;
+	if (active) {
+		while ((bi + 1) * (bi + 2) / 2 <= tid) bi++;
+		bj = tid - bi * (bi + 1) / 2;
 	}
-	__syncthreads();
+	double a[8][8];
+	if (active) {
+#pragma unroll
+		for (int r = 0; r < 8; r++) {
+			const double *src = A + (size_t)(bi * 8 + r) * ld + bj * 8;
+#pragma unroll
+			for (int c = 0; c < 8; c += 2) {
+				double2 v = *reinterpret_cast<const double2 *>(src + c);
+				a[r][c] = v.x;
+				a[r][c + 1] = v.y;
+			}
+		}
+	}
+	// strictly upper sub-blocks of both outputs are zero
+	for (int idx = tid; idx < TB * TB; idx += POTF2_THREADS) {
+		const int i = idx >> 7, c = idx & 127;
+		if ((c >> 3) > (i >> 3)) {
+			Lg[(size_t)i * ld + c] = 0.0;
+			Wg[(size_t)i * ld + c] = 0.0;
+		}
+	}
 	double logsum = 0.0;
 	int bad = 0;
-	for (int j = 0; j < TB; j++) {
-		const double ajj = S[j * PS + j];
-		const bool ok = (ajj > 0.0) && (ajj < 1.0e300);
-		if (!ok) bad = 1;
-		const double ljj = sqrt(ok ? ajj : 1.0);
-		const double inv = 1.0 / ljj;
-		if (tid == 0) logsum += log(ljj);
-		if (tid < TB) {
-			const int i = tid;
-			if (i > j) {
-				double l = S[i * PS + j] * inv;
-				lcol[i] = l;
-				S[j * PS + i] = l;  // stash L(i, j) transposed
-			} else if (i == j) {
-				ldiag[j] = ljj;
+	for (int jb = 0; jb < 16; jb++) {
+#pragma unroll
+		for (int jj = 0; jj < 8; jj++) {
+			const int j = jb * 8 + jj;
+			double *cb = colbuf + (j & 1) * TB;
+			double *rb = rowbuf + (j & 1) * TB;
+			if (active) {
+				if (bj == jb) {
+#pragma unroll
+					for (int r = 0; r < 8; r++) cb[bi * 8 + r] = a[r][jj];
+				}
+				if (bi == jb) {
+#pragma unroll
+					for (int c = 0; c < 8; c++) rb[bj * 8 + c] = a[jj][c];
+				}
 			}
-		} else {
-			const int c = tid - TB;
-			if (c < j) {
-				double e = S[j * PS + c] * inv;
-				vrow[c] = e;
-			} else if (c == j) {
-				vrow[j] = inv;
+			__syncthreads();
+			const double p = cb[j];
+			const bool ok = (p > 0.0) && (p < 1.0e300);
+			if (!ok) bad = 1;
+			const double sq = sqrt(ok ? p : 1.0);
+			const double isq = 1.0 / sq;
+			const double ip = isq * isq;
+			if (tid == 0) logsum += log(sq);
+			if (active && bi >= jb) {
+				if (bj == jb) {
+#pragma unroll
+					for (int r = 0; r < 8; r++) {
+						const int gi = bi * 8 + r;
+						double l = a[r][jj] * isq;
+						if (gi == j) l = sq;
+						if (gi >= j) Lp[gi * (gi + 1) / 2 + j] = l;
+					}
+				}
+				double v[8];
+#pragma unroll
+				for (int c = 0; c < 8; c++) {
+					const int gc = bj * 8 + c;
+					if (bj < jb) v[c] = rb[gc] * ip;
+					else if (bj > jb) v[c] = cb[gc] * ip;
+					else v[c] = (c < jj) ? rb[gc] * ip : ((c == jj) ? ip : cb[gc] * ip);
+				}
+				if (bi > jb) {
+#pragma unroll
+					for (int r = 0; r < 8; r++) {
+						const double l = cb[bi * 8 + r];
+#pragma unroll
+						for (int c = 0; c < 8; c++) {
+							if (c == jj) a[r][c] = (bj == jb) ? -l * v[c] : a[r][c] - l * v[c];
+							else a[r][c] -= l * v[c];
+						}
+					}
+				} else {
+					// the diagonal-row sub-blocks: rows below j are updated, row j becomes final
+#pragma unroll
+					for (int r = 0; r < 8; r++) {
+						if (r > jj) {
+							const double l = cb[bi * 8 + r];
+#pragma unroll
+							for (int c = 0; c < 8; c++) {
+								if (c == jj) a[r][c] = (bj == jb) ? -l * v[c] : a[r][c] - l * v[c];
+								else a[r][c] -= l * v[c];
+							}
+						} else if (r == jj) {
+#pragma unroll
+							for (int c = 0; c < 8; c++) {
+								if (bj < jb || c < jj) a[r][c] *= isq;
+								else if (c == jj) a[r][c] = isq;
+							}
+						}
+					}
+				}
 			}
 		}
-		__syncthreads();
-		// row j of the inverse becomes final; rows i > j get  S(i, c) -= L(i, j) * v(c)
-		if (tid <= j) S[j * PS + tid] = vrow[tid];
-		for (int i = j + 1 + warp; i < TB; i += POTF2_THREADS / 32) {
-			const double li = lcol[i];
-			double *Si = S + i * PS;
-			for (int c = lane; c <= i; c += 32) {
-				if (c < j) Si[c] -= li * vrow[c];
-				else if (c == j) Si[c] = -li * vrow[j];
-				else Si[c] -= li * lcol[c];
-			}
-		}
-		__syncthreads();
 	}
+	__syncthreads();
 	if (tid == 0) {
 		logdet_parts[(size_t)b * nblk + kblk] = logsum;
 		if (bad) info[b] = 1;
 	}
+	if (active) {
+#pragma unroll
+		for (int r = 0; r < 8; r++) {
+			const int gi = bi * 8 + r;
+			double *dst = Wg + (size_t)gi * ld + bj * 8;
+#pragma unroll
+			for (int c = 0; c < 8; c += 2) {
+				double2 v;
+				v.x = (bj * 8 + c <= gi) ? a[r][c] : 0.0;
+				v.y = (bj * 8 + c + 1 <= gi) ? a[r][c + 1] : 0.0;
+				*reinterpret_cast<double2 *>(dst + c) = v;
+			}
+		}
+	}
 	for (int idx = tid; idx < TB * TB; idx += POTF2_THREADS) {
-		int i = idx >> 7, c = idx & 127;
-		double l, w;
-		if (c < i) { l = S[c * PS + i]; w = S[i * PS + c]; }
-		else if (c == i) { l = ldiag[i]; w = S[i * PS + i]; }
-		else { l = 0.0; w = 0.0; }
-		A[(size_t)i * ld + c] = l;
-		W[(size_t)i * ld + c] = w;
+		const int i = idx >> 7, c = idx & 127;
+		if ((c >> 3) <= (i >> 3)) Lg[(size_t)i * ld + c] = (c <= i) ? Lp[i * (i + 1) / 2 + c] : 0.0;
 	}
 }
 

@@ -32,6 +32,15 @@ def _oracle(X, y, kernel, order):
     return PortOracle(X, y, kernel, order)
 
 
+def _sigma2_scale(X, y, kernel, order, theta_less_amp):
+    o = _oracle(X, y, kernel, order)
+    if kernel == 1:
+        C = o.cov_matrix(np.concatenate([[0.0], theta_less_amp]))
+    else:  # deviation D-2: unit amplitude, exp-scaled nugget
+        C = o.cov_matrix(np.array([1.0, np.exp(theta_less_amp[0]), theta_less_amp[1]]))
+    return abs(float(y @ np.linalg.solve(C, y))) / len(y)
+
+
 def _grad_err(g, gref):
     scale = np.maximum(np.abs(gref), 1e-3 * np.max(np.abs(gref)) + 1e-300)
     return float(np.max(np.abs(g - gref) / scale))
@@ -60,7 +69,9 @@ def test_golden_fixture(ctx, name):
         assert r["status"] == 0
         assert relerr(r["negL"], c["negL_logsum"]) < TOL
         assert relerr(r["logdet"], c["logdet"]) < TOL
-        assert relerr(r["sigma2"], c["sigma2"]) < TOL
+        # sigma2 = y.C^-1 (y - H beta) / n is a cancellation (pure rounding noise when y lies in the span of the
+        # regression basis, e.g. uni-2d order 2): judged relative to its constituent |y.C^-1 y| / n
+        assert abs(r["sigma2"] - c["sigma2"]) < TOL * _sigma2_scale(c["X"], c["y"], c["kernel"], c["order"], c["theta_less_amp"])
         assert relerr(r["beta"], c["beta"], 1e-6) < TOL
         assert _grad_err(r["grad"], c["grad"]) < TOL
         if np.isfinite(c["negL_literal"]):
@@ -88,7 +99,7 @@ def test_synthetic_vs_oracle(ctx, n, d, order, kernel):
         ref = o.loglik_grad(ths[b])
         assert r["status"][b] == ref["status"] == 0
         assert relerr(r["negL"][b], ref["negL"]) < TOL
-        assert relerr(r["sigma2"][b], ref["sigma2"]) < TOL
+        assert abs(r["sigma2"][b] - ref["sigma2"]) < TOL * _sigma2_scale(X, y, kernel, order, ths[b])
         assert _grad_err(r["grad"][b], ref["grad"]) < TOL
     # value-only path returns the same value
     r2 = m.loglik_grad_batch(ths, want_grad=False)
@@ -145,10 +156,11 @@ def test_not_positive_definite_reports_edom(ctx):
     """evalFnMulti returns NaN when the Cholesky fails (maxmultimin.c:327-350); the engine flags the
     point and carries on with the rest of the batch."""
     from madaiemulator_b200 import engine
-    X = np.array([[0.0], [1e-12], [1.0], [2.0]])  # two numerically identical points
+    X = np.array([[0.0], [0.5], [1.0], [2.0]])
     y = np.array([1.0, 1.1, 0.3, 0.2])
     m = engine.Model(ctx, X, y, 1, 0, max_slots=2)
-    ths = np.array([[-800.0, 0.0], [-3.0, 0.0]])  # nugget exp(-800) = 0 -> singular; second point fine
+    # nugget exp(-800) = 0 and length exp(20): C is the all-ones matrix -> singular; second point fine
+    ths = np.array([[-800.0, 20.0], [-3.0, 0.0]])
     r = m.loglik_grad_batch(ths)
     assert r["status"][0] == engine.EDOM and np.isnan(r["negL"][0]) and np.all(np.isnan(r["grad"][0]))
     assert r["status"][1] == 0 and np.isfinite(r["negL"][1])

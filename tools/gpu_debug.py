@@ -37,11 +37,11 @@ for (n, d, order) in [(100, 3, 1), (300, 6, 2), (700, 10, 0)]:
 # timing at n=4096
 n, d = 4096, 10
 X = ds.synthetic_design(n, d); y = ds.synthetic_response(X)
-m = engine.Model(ctx, X, y, 1, 0, max_slots=8)
-th = np.tile(ds.default_theta_less_amp(d), (8, 1))
-for g in (1, 2):
+m = engine.Model(ctx, X, y, 1, 0, max_slots=16)
+th = np.tile(ds.default_theta_less_amp(d), (16, 1))
+for g in (1, 2, 4):
     ctx.set_groups(g)
-    for B in (1, 8):
+    for B in (1, 8, 16):
         m.loglik_grad_batch(th[:B])
         t0 = time.time(); r = m.loglik_grad_batch(th[:B]); t1 = time.time()
         print("n=4096 groups", g, "B", B, "ms", (t1 - t0) * 1e3, "evals/s", B / (t1 - t0), "negL", r["negL"][0], "status", r["status"][0])
