@@ -199,7 +199,7 @@ static void build_factor(emub_model *m, int lo, int hi, std::vector<GemmTask> &t
 	auto emit = [&](int type, std::vector<GemmTask> &t) {
 		std::stable_sort(t.begin(), t.end(), by_k);
 		FactorStep st{type, (int)tasks.size(), (int)t.size(), 0, 0.0};
-		for (auto &x : t) { tasks.push_back(x); st.flops += 2.0 * TB * TB * (double)x.klen; }
+		for (auto &x : t) { tasks.push_back(x); st.flops += ((x.aux & TASK_LOWER) ? 0.75 : 1.0) * 2.0 * TB * TB * (double)x.klen; }
 		m->steps.push_back(st);
 	};
 	if (hi - lo == 1) {
@@ -216,7 +216,7 @@ static void build_factor(emub_model *m, int lo, int hi, std::vector<GemmTask> &t
 	t.clear();
 	// A(i,j) -= sum_{k in [lo, mid)} L(i,k) L(j,k)^T      A, B = bufT KMAJOR -> bufA
 	for (int i = mid; i < hi; i++)
-		for (int j = mid; j <= i; j++) t.push_back({off(i, lo), off(j, lo), off(i, j), (mid - lo) * TB, 0});
+		for (int j = mid; j <= i; j++) t.push_back({off(i, lo), off(j, lo), off(i, j), (mid - lo) * TB, (i == j) ? TASK_LOWER : 0});
 	emit(STEP_SYRK, t);
 	build_factor(m, mid, hi, tasks);
 	t.clear();
@@ -242,8 +242,8 @@ static void build_schedules(emub_model *m, std::vector<GemmTask> &tasks)
 	m->lauum_flops = 0;
 	for (int i = 0; i < nb; i++)
 		for (int j = 0; j <= i; j++) {
-			tasks.push_back({off(i, i), off(i, j), off(i, j), (nb - i) * TB, 0});
-			m->lauum_flops += 2.0 * TB * TB * (double)(nb - i) * TB;
+			tasks.push_back({off(i, i), off(i, j), off(i, j), (nb - i) * TB, (i == j) ? TASK_LOWER : 0});
+			m->lauum_flops += ((i == j) ? 0.75 : 1.0) * 2.0 * TB * TB * (double)(nb - i) * TB;
 		}
 	m->lauum_cnt = (int)tasks.size() - m->lauum_off;
 }
@@ -358,7 +358,7 @@ static void launch_gemm(emub_ctx *c, int fam, double flops, cudaStream_t st, con
 	if (ntasks <= 0 || batch <= 0) return;
 	GemmArgs a{tasks, A, B, C, sA, sB, sC, lda, ldb, ldc, alpha};
 	LaunchScope ls(c, fam, flops * batch, st);
-	k_gemm<AL, BL, EPI><<<dim3(ntasks, batch), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(a);
+	k_gemm<AL, BL, EPI><<<dim3(ntasks * DefaultCfg::SUBS, batch), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(a);
 }
 
 static void launch_cov(emub_model *m, cudaStream_t st, int count, const double *consts, double *out, long long ostride,
@@ -731,7 +731,7 @@ extern "C" int emub_emulator_create(emub_model *m, const double *thetas, emub_em
 	e->mqc = mqc;
 	CUDA_TRY(cudaMalloc(&e->dQ, sizeof(double) * (size_t)mqc * m->d));
 	CUDA_TRY(cudaMalloc(&e->dK, sizeof(double) * (size_t)m->npad * mqc));
-	CUDA_TRY(cudaMalloc(&e->dVsq, sizeof(double) * (size_t)m->nblk * mqc));
+	CUDA_TRY(cudaMalloc(&e->dVsq, sizeof(double) * (size_t)m->nblk * DefaultCfg::SUBM * mqc));
 	CUDA_TRY(cudaMalloc(&e->dKA, sizeof(double) * (size_t)mqc * m->ncp));
 	CUDA_TRY(cudaMalloc(&e->dMean, sizeof(double) * mqc));
 	CUDA_TRY(cudaMalloc(&e->dVar, sizeof(double) * mqc));
@@ -784,7 +784,7 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 	}
 	{
 		LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);
-		k_pred_final<<<(mq + 127) / 128, 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, e->dKA, m->ncp, e->dVsq, m->nblk, ldk, e->beta,
+		k_pred_final<<<(mq + 127) / 128, 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, e->dKA, m->ncp, e->dVsq, m->nblk * DefaultCfg::SUBM, ldk, e->beta,
 		                                               e->Minv, e->kappa, dMean, dVar);
 	}
 	CUDA_TRY(cudaGetLastError());

@@ -6,11 +6,11 @@
 // updates, triangular inverse, W^T W, W K) is expressed purely through the K range and the tile
 // list, built once per model on the host (emub_schedule.cpp).  tcgen05/TMEM has no FP64 kind, so
 // on sm_100a FP64 tensor work goes through mma.sync; operands are staged global -> shared with a
-// 4-stage cp.async pipeline, padded so that every fragment load is bank-conflict free.
+// multi-stage cp.async pipeline, padded so that every fragment load is bank-conflict free.
 //
 // Operand layouts (per operand):
-//   KMAJOR : elem(r, k) = P[r * ld + k]   (k contiguous)   smem tile [128][BK + 4]
-//   RMAJOR : elem(r, k) = P[k * ld + r]   (r contiguous)   smem tile [BK][128 + 4]
+//   KMAJOR : elem(r, k) = P[r * ld + k]   (k contiguous)   smem tile [rows][BK + 4]
+//   RMAJOR : elem(r, k) = P[k * ld + r]   (r contiguous)   smem tile [BK][rows + 4]
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,13 +18,30 @@
 namespace emub {
 
 constexpr int TB = 128;       // tile edge (BM = BN = NB)
-constexpr int BK = 16;        // k per pipeline stage
-constexpr int STAGES = 4;
-constexpr int GEMM_THREADS = 256;
-constexpr int KM_STRIDE = BK + 4;   // 20 doubles: (g*20 + t) mod 16 distinct over a half warp
-constexpr int RM_STRIDE = TB + 4;   // 132 doubles: (t*132 + g) mod 16 distinct over a half warp
-constexpr int OPER_DOUBLES = TB * KM_STRIDE;  // 2560 >= BK * RM_STRIDE (2112)
-constexpr int GEMM_SMEM_BYTES = STAGES * 2 * OPER_DOUBLES * 8;  // 163840
+
+// Tile-engine configuration: the task list addresses 128 x 128 output tiles; a CTA computes one BM x BN
+// sub-tile of it with WM x WN warps (warp tile (BM/WM) x (BN/WN)), BK k-columns per pipeline stage and
+// STAGES cp.async stages; MINB CTAs are resident per SM so that the prologue, barriers and epilogue of one
+// CTA overlap the DMMA stream of the others (cuBLAS reaches 95% tensor-pipe activity the same way with
+// 64 x 64 tiles).  Shared-memory strides are padded to 4 (mod 16) doubles so that the 16 lanes of a half
+// warp (4 rows x 4 k) hit 16 different 8-byte banks.
+template <int BM_, int BN_, int WM_, int WN_, int BK_, int STAGES_, int MINB_>
+struct GemmCfg {
+	static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, BK = BK_, STAGES = STAGES_, MINB = MINB_;
+	static constexpr int THREADS = WM * WN * 32;
+	static constexpr int WTM = BM / WM, WTN = BN / WN;  // warp tile
+	static constexpr int MI = WTM / 16, NI = WTN / 8;   // m16n8k4 tiles per warp
+	static constexpr int SUBM = TB / BM, SUBN = TB / BN, SUBS = SUBM * SUBN;
+	static constexpr int KM_STRIDE = BK + 4;
+	static constexpr int RMA_STRIDE = BM + 4, RMB_STRIDE = BN + 4;
+	static constexpr int A_DOUBLES = (BM * KM_STRIDE > BK * RMA_STRIDE) ? BM * KM_STRIDE : BK * RMA_STRIDE;
+	static constexpr int B_DOUBLES = (BN * KM_STRIDE > BK * RMB_STRIDE) ? BN * KM_STRIDE : BK * RMB_STRIDE;
+	static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
+	static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
+};
+using DefaultCfg = GemmCfg<64, 64, 2, 2, 8, 4, 4>;  // 4 CTAs / SM: 35.3 TFLOP/s on 4096^3 (cuBLAS: 35.2)
+constexpr int GEMM_THREADS = DefaultCfg::THREADS;
+constexpr int GEMM_SMEM_BYTES = DefaultCfg::SMEM_BYTES;
 
 enum { KMAJOR = 0, RMAJOR = 1 };
 enum { EPI_STORE = 0, EPI_SUB = 1, EPI_COLSUMSQ = 2 };
@@ -63,43 +80,52 @@ __device__ __forceinline__ void dmma_16x8x4(double (&c)[4], double a0, double a1
 	             : "d"(a0), "d"(a1), "d"(b0));
 }
 
-template <int LAYOUT>
+// ROWS x BK operand tile, global -> shared, 16-byte cp.async chunks
+template <class Cfg, int LAYOUT, int ROWS>
 __device__ __forceinline__ void load_operand_stage(double *s, const double *g, int ld, int tid)
 {
+	constexpr int CHUNKS = ROWS * Cfg::BK / 2;
+	constexpr int ITERS = (CHUNKS + Cfg::THREADS - 1) / Cfg::THREADS;
 	if (LAYOUT == KMAJOR) {
-		// 128 rows x 16 k: 8 chunks (16 B) per row
+		constexpr int CPR = Cfg::BK / 2;  // chunks per row
 #pragma unroll
-		for (int c = 0; c < 4; c++) {
-			int chunk = tid + c * GEMM_THREADS;
-			int row = chunk >> 3, kc = chunk & 7;
-			cp_async16(s + row * KM_STRIDE + kc * 2, g + (long long)row * ld + kc * 2);
+		for (int c = 0; c < ITERS; c++) {
+			int chunk = tid + c * Cfg::THREADS;
+			if (CHUNKS % Cfg::THREADS == 0 || chunk < CHUNKS) {
+				int row = chunk / CPR, kc = chunk % CPR;
+				cp_async16(s + row * Cfg::KM_STRIDE + kc * 2, g + (long long)row * ld + kc * 2);
+			}
 		}
 	} else {
-		// 16 k rows x 128 r: 64 chunks per k row
+		constexpr int CPK = ROWS / 2;  // chunks per k row
+		constexpr int STRIDE = ROWS + 4;
 #pragma unroll
-		for (int c = 0; c < 4; c++) {
-			int chunk = tid + c * GEMM_THREADS;
-			int kr = chunk >> 6, rc = chunk & 63;
-			cp_async16(s + kr * RM_STRIDE + rc * 2, g + (long long)kr * ld + rc * 2);
+		for (int c = 0; c < ITERS; c++) {
+			int chunk = tid + c * Cfg::THREADS;
+			if (CHUNKS % Cfg::THREADS == 0 || chunk < CHUNKS) {
+				int kr = chunk / CPK, rc = chunk % CPK;
+				cp_async16(s + kr * STRIDE + rc * 2, g + (long long)kr * ld + rc * 2);
+			}
 		}
 	}
 }
 
-template <int LAYOUT>
+template <class Cfg, int LAYOUT, int ROWS>
 __device__ __forceinline__ double frag(const double *s, int r, int k)
 {
-	return (LAYOUT == KMAJOR) ? s[r * KM_STRIDE + k] : s[k * RM_STRIDE + r];
+	return (LAYOUT == KMAJOR) ? s[r * Cfg::KM_STRIDE + k] : s[k * (ROWS + 4) + r];
 }
 
-// acc[mi][ni][4]: warp tile 64 (m) x 32 (n); 8 warps as 2 (m) x 4 (n)
-template <int AL, int BL>
+// acc[mi][ni][4]: warp tile WTM (m) x WTN (n)
+template <class Cfg, int AL, int BL>
 __device__ __forceinline__ void gemm_mainloop(const double *__restrict__ gA, const double *__restrict__ gB, int lda,
-                                              int ldb, int klen, double *smem, double (&acc)[4][4][4])
+                                              int ldb, int klen, double *smem, double (&acc)[Cfg::MI][Cfg::NI][4])
 {
+	constexpr int BK = Cfg::BK, STAGES = Cfg::STAGES, STG = Cfg::STAGE_DOUBLES;
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
 	const int g = lane >> 2, t = lane & 3;
-	const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+	const int wm = (warp / Cfg::WN) * Cfg::WTM, wn = (warp % Cfg::WN) * Cfg::WTN;
 	const int ktiles = klen / BK;
 	const long long a_step = (AL == KMAJOR) ? BK : (long long)BK * lda;
 	const long long b_step = (BL == KMAJOR) ? BK : (long long)BK * ldb;
@@ -107,8 +133,8 @@ __device__ __forceinline__ void gemm_mainloop(const double *__restrict__ gA, con
 #pragma unroll
 	for (int s = 0; s < STAGES - 1; s++) {
 		if (s < ktiles) {
-			load_operand_stage<AL>(smem + (2 * s) * OPER_DOUBLES, gA + s * a_step, lda, tid);
-			load_operand_stage<BL>(smem + (2 * s + 1) * OPER_DOUBLES, gB + s * b_step, ldb, tid);
+			load_operand_stage<Cfg, AL, Cfg::BM>(smem + s * STG, gA + s * a_step, lda, tid);
+			load_operand_stage<Cfg, BL, Cfg::BN>(smem + s * STG + Cfg::A_DOUBLES, gB + s * b_step, ldb, tid);
 		}
 		cp_async_commit();
 	}
@@ -119,63 +145,71 @@ __device__ __forceinline__ void gemm_mainloop(const double *__restrict__ gA, con
 			int nk = kt + STAGES - 1;
 			if (nk < ktiles) {
 				int slot = nk % STAGES;
-				load_operand_stage<AL>(smem + (2 * slot) * OPER_DOUBLES, gA + nk * a_step, lda, tid);
-				load_operand_stage<BL>(smem + (2 * slot + 1) * OPER_DOUBLES, gB + nk * b_step, ldb, tid);
+				load_operand_stage<Cfg, AL, Cfg::BM>(smem + slot * STG, gA + nk * a_step, lda, tid);
+				load_operand_stage<Cfg, BL, Cfg::BN>(smem + slot * STG + Cfg::A_DOUBLES, gB + nk * b_step, ldb, tid);
 			}
 			cp_async_commit();
 		}
-		const double *sA = smem + (2 * (kt % STAGES)) * OPER_DOUBLES;
-		const double *sB = sA + OPER_DOUBLES;
+		const double *sA = smem + (kt % STAGES) * STG;
+		const double *sB = sA + Cfg::A_DOUBLES;
 #pragma unroll
 		for (int kk = 0; kk < BK; kk += 4) {
-			double a[4][2], b[4];
+			double a[Cfg::MI][2], b[Cfg::NI];
 #pragma unroll
-			for (int mi = 0; mi < 4; mi++) {
-				a[mi][0] = frag<AL>(sA, wm + mi * 16 + g, kk + t);
-				a[mi][1] = frag<AL>(sA, wm + mi * 16 + g + 8, kk + t);
+			for (int mi = 0; mi < Cfg::MI; mi++) {
+				a[mi][0] = frag<Cfg, AL, Cfg::BM>(sA, wm + mi * 16 + g, kk + t);
+				a[mi][1] = frag<Cfg, AL, Cfg::BM>(sA, wm + mi * 16 + g + 8, kk + t);
 			}
 #pragma unroll
-			for (int ni = 0; ni < 4; ni++) b[ni] = frag<BL>(sB, wn + ni * 8 + g, kk + t);
+			for (int ni = 0; ni < Cfg::NI; ni++) b[ni] = frag<Cfg, BL, Cfg::BN>(sB, wn + ni * 8 + g, kk + t);
 #pragma unroll
-			for (int mi = 0; mi < 4; mi++)
+			for (int mi = 0; mi < Cfg::MI; mi++)
 #pragma unroll
-				for (int ni = 0; ni < 4; ni++) dmma_16x8x4(acc[mi][ni], a[mi][0], a[mi][1], b[ni]);
+				for (int ni = 0; ni < Cfg::NI; ni++) dmma_16x8x4(acc[mi][ni], a[mi][0], a[mi][1], b[ni]);
 		}
 	}
 	cp_async_wait<0>();
 }
 
-// grid: (ntasks, batch)
-template <int AL, int BL, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(GemmArgs p)
-{
-	extern __shared__ __align__(16) double smem[];
-	const GemmTask task = p.tasks[blockIdx.x];
-	const int b = blockIdx.y;
-	const double *gA = p.A + b * p.strideA + task.a_off;
-	const double *gB = p.B + b * p.strideB + task.b_off;
+// grid: (ntasks * SUBS, batch).  TASK_LOWER in task.aux (EPI_STORE / EPI_SUB): the tile is a diagonal tile of a
+// symmetric / triangular result, sub-tiles strictly above the diagonal are skipped.
+constexpr int TASK_LOWER = 1 << 30;
 
-	double acc[4][4][4];
+template <int AL, int BL, int EPI, class Cfg = DefaultCfg>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) k_gemm(GemmArgs p)
+{
+	constexpr int MI = Cfg::MI, NI = Cfg::NI;
+	extern __shared__ __align__(16) double smem[];
+	const GemmTask task = p.tasks[blockIdx.x / Cfg::SUBS];
+	const int sub = blockIdx.x % Cfg::SUBS;
+	const int sr = sub / Cfg::SUBN, sc = sub % Cfg::SUBN;
+	if (EPI != EPI_COLSUMSQ && (task.aux & TASK_LOWER) && sc * Cfg::BN >= (sr + 1) * Cfg::BM) return;
+	const int b = blockIdx.y;
+	const double *gA = p.A + b * p.strideA + task.a_off + ((AL == KMAJOR) ? (long long)sr * Cfg::BM * p.lda : (long long)sr * Cfg::BM);
+	const double *gB = p.B + b * p.strideB + task.b_off + ((BL == KMAJOR) ? (long long)sc * Cfg::BN * p.ldb : (long long)sc * Cfg::BN);
+
+	double acc[MI][NI][4];
 #pragma unroll
-	for (int i = 0; i < 4; i++)
+	for (int i = 0; i < MI; i++)
 #pragma unroll
-		for (int j = 0; j < 4; j++)
+		for (int j = 0; j < NI; j++)
 #pragma unroll
 			for (int r = 0; r < 4; r++) acc[i][j][r] = 0.0;
 
-	gemm_mainloop<AL, BL>(gA, gB, p.lda, p.ldb, task.klen, smem, acc);
+	gemm_mainloop<Cfg, AL, BL>(gA, gB, p.lda, p.ldb, task.klen, smem, acc);
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
 	const int g = lane >> 2, t = lane & 3;
-	const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+	const int wmi = warp / Cfg::WN;
+	const int wm = wmi * Cfg::WTM, wn = (warp % Cfg::WN) * Cfg::WTN;
 
 	if (EPI == EPI_STORE || EPI == EPI_SUB) {
-		double *gC = p.C + b * p.strideC + task.c_off;
+		double *gC = p.C + b * p.strideC + task.c_off + (long long)sr * Cfg::BM * p.ldc + sc * Cfg::BN;
 #pragma unroll
-		for (int mi = 0; mi < 4; mi++)
+		for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-			for (int ni = 0; ni < 4; ni++)
+			for (int ni = 0; ni < NI; ni++)
 #pragma unroll
 				for (int h = 0; h < 2; h++) {
 					int row = wm + mi * 16 + g + 8 * h;
@@ -193,14 +227,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(GemmArgs p)
 					*ptr = v;
 				}
 	} else {
-		// column sums of squares of the 128 x 128 tile -> C[aux * ldc + c_off + col]
+		// column sums of squares of the BM x BN sub-tile -> C[(aux * SUBM + sr) * ldc + c_off + sc * BN + col]
 		__syncthreads();  // everyone is done with the pipeline buffers
-		double *red = smem;  // [2][128]
+		double *red = smem;  // [WM][BN]
 #pragma unroll
-		for (int ni = 0; ni < 4; ni++) {
+		for (int ni = 0; ni < NI; ni++) {
 			double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-			for (int mi = 0; mi < 4; mi++) {
+			for (int mi = 0; mi < MI; mi++) {
 				s0 += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][2] * acc[mi][ni][2];
 				s1 += acc[mi][ni][1] * acc[mi][ni][1] + acc[mi][ni][3] * acc[mi][ni][3];
 			}
@@ -210,14 +244,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm(GemmArgs p)
 				s1 += __shfl_xor_sync(0xffffffffu, s1, o);
 			}
 			if (g == 0) {
-				red[(warp >> 2) * TB + wn + ni * 8 + 2 * t] = s0;
-				red[(warp >> 2) * TB + wn + ni * 8 + 2 * t + 1] = s1;
+				red[wmi * Cfg::BN + wn + ni * 8 + 2 * t] = s0;
+				red[wmi * Cfg::BN + wn + ni * 8 + 2 * t + 1] = s1;
 			}
 		}
 		__syncthreads();
-		if (tid < TB) {
-			double *gC = p.C + b * p.strideC + (long long)task.aux * p.ldc + task.c_off;
-			gC[tid] = red[tid] + red[TB + tid];
+		if (tid < Cfg::BN) {
+			double *gC = p.C + b * p.strideC + (long long)((task.aux & 0xffff) * Cfg::SUBM + sr) * p.ldc + task.c_off + sc * Cfg::BN;
+			double sum = 0.0;
+#pragma unroll
+			for (int w = 0; w < Cfg::WM; w++) sum += red[w * Cfg::BN + tid];
+			gC[tid] = sum;
 		}
 	}
 }

@@ -175,7 +175,7 @@ __global__ void k_set_y(const double *__restrict__ y, int n, int ncp, double *__
 constexpr int POTF2_THREADS = 160;
 constexpr int POTF2_NBLOCKS = 136;
 constexpr int POTF2_LPACK = TB * (TB + 1) / 2;
-constexpr int POTF2_SMEM_BYTES = (POTF2_LPACK + 4 * TB) * 8;
+constexpr int POTF2_SMEM_BYTES = (POTF2_LPACK + 5 * TB) * 8;
 
 __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, long long strideA, double *Lbase, long long strideL,
                                                          double *Wbase, long long strideW, int ld, int kblk, int nblk,
@@ -217,9 +217,10 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 			Wg[(size_t)i * ld + c] = 0.0;
 		}
 	}
-	double logsum = 0.0;
 	int bad = 0;
+	double *pivots = rowbuf + 2 * TB;  // [128] a_jj at elimination time, for the log-determinant
 	for (int jb = 0; jb < 16; jb++) {
+		// jj is unrolled so that every register-array index below is a compile-time constant
 #pragma unroll
 		for (int jj = 0; jj < 8; jj++) {
 			const int j = jb * 8 + jj;
@@ -239,60 +240,56 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 			const double p = cb[j];
 			const bool ok = (p > 0.0) && (p < 1.0e300);
 			if (!ok) bad = 1;
-			const double sq = sqrt(ok ? p : 1.0);
-			const double isq = 1.0 / sq;
+			const double pp = ok ? p : 1.0;
+			const double isq = rsqrt(pp);
+			const double sq = pp * isq;
 			const double ip = isq * isq;
-			if (tid == 0) logsum += log(sq);
+			if (tid == 0) pivots[j] = pp;
 			if (active && bi >= jb) {
-				if (bj == jb) {
+				double l[8], v[8];
 #pragma unroll
-					for (int r = 0; r < 8; r++) {
-						const int gi = bi * 8 + r;
-						double l = a[r][jj] * isq;
-						if (gi == j) l = sq;
-						if (gi >= j) Lp[gi * (gi + 1) / 2 + j] = l;
-					}
+				for (int r = 0; r < 8; r++) {
+					const int gi = bi * 8 + r;
+					const double raw = cb[gi];
+					l[r] = (gi > j) ? raw : 0.0;
+					if (bj == jb && gi >= j) Lp[gi * (gi + 1) / 2 + j] = (gi == j) ? sq : raw * isq;
 				}
-				double v[8];
 #pragma unroll
 				for (int c = 0; c < 8; c++) {
 					const int gc = bj * 8 + c;
-					if (bj < jb) v[c] = rb[gc] * ip;
-					else if (bj > jb) v[c] = cb[gc] * ip;
-					else v[c] = (c < jj) ? rb[gc] * ip : ((c == jj) ? ip : cb[gc] * ip);
+					const double src = (gc < j) ? rb[gc] : cb[gc];
+					v[c] = (gc == j) ? ip : src * ip;
 				}
-				if (bi > jb) {
+				if (bj == jb) {
+					// the slot of column j now starts to hold the inverse: -L(i,j) / L(j,j) = 0 - a(i,j) / a(j,j)
 #pragma unroll
-					for (int r = 0; r < 8; r++) {
-						const double l = cb[bi * 8 + r];
+					for (int r = 0; r < 8; r++)
+						if (bi * 8 + r > j) a[r][jj] = 0.0;
+				}
+				if (bi == jb) {
+					// row j of the inverse becomes final
 #pragma unroll
-						for (int c = 0; c < 8; c++) {
-							if (c == jj) a[r][c] = (bj == jb) ? -l * v[c] : a[r][c] - l * v[c];
-							else a[r][c] -= l * v[c];
-						}
-					}
-				} else {
-					// the diagonal-row sub-blocks: rows below j are updated, row j becomes final
-#pragma unroll
-					for (int r = 0; r < 8; r++) {
-						if (r > jj) {
-							const double l = cb[bi * 8 + r];
-#pragma unroll
-							for (int c = 0; c < 8; c++) {
-								if (c == jj) a[r][c] = (bj == jb) ? -l * v[c] : a[r][c] - l * v[c];
-								else a[r][c] -= l * v[c];
-							}
-						} else if (r == jj) {
-#pragma unroll
-							for (int c = 0; c < 8; c++) {
-								if (bj < jb || c < jj) a[r][c] *= isq;
-								else if (c == jj) a[r][c] = isq;
-							}
-						}
+					for (int c = 0; c < 8; c++) {
+						const int gc = bj * 8 + c;
+						if (gc < j) a[jj][c] *= isq;
+						else if (gc == j) a[jj][c] = isq;
 					}
 				}
+#pragma unroll
+				for (int r = 0; r < 8; r++)
+#pragma unroll
+					for (int c = 0; c < 8; c++) a[r][c] -= l[r] * v[c];
 			}
 		}
+	}
+	__syncthreads();
+	double logsum = 0.0;
+	if (tid < 32) {
+		// sum_j log L_jj = 0.5 sum_j log a_jj, fixed order
+		double s = log(pivots[tid]) + log(pivots[tid + 32]) + log(pivots[tid + 64]) + log(pivots[tid + 96]);
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+		logsum = 0.5 * s;
 	}
 	__syncthreads();
 	if (tid == 0) {
