@@ -280,3 +280,84 @@ class Emulator:
             self.close()
         except Exception:
             pass
+
+
+# ---- host C layer (madaiemulator_b200/host/libemuhost.so): restart driver over the batched evaluator ----------
+HOST_LIB_PATH = os.path.join(_HERE, "host", "libemuhost.so")
+HOST_SYMBOLS = ["emub_estimate_default_opts", "emub_sample_scales", "emub_optimization_ranges", "emub_random_init",
+                "emub_estimate_thetas", "emub_estimate_thetas_from"]
+
+
+class EstimateOpts(ctypes.Structure):
+    _fields_ = [("max_tries", _ci), ("nchains", _ci), ("seed", ctypes.c_ulonglong), ("step_size", ctypes.c_double),
+                ("tol", ctypes.c_double), ("eps_abs", ctypes.c_double), ("step_max", _ci)]
+
+
+class EstimateStats(ctypes.Structure):
+    _fields_ = [("evaluations", _ll), ("batches", _ll), ("success_count", _ci), ("finite_count", _ci)]
+
+
+_hostlib = None
+
+
+def host_lib():
+    global _hostlib
+    if _hostlib is not None:
+        return _hostlib
+    if not os.path.exists(HOST_LIB_PATH):
+        raise RuntimeError("host layer %s is missing: run `make -C madaiemulator_b200/host`" % HOST_LIB_PATH)
+    lib()  # libemub.so first (the host layer links against it)
+    H = ctypes.CDLL(HOST_LIB_PATH)
+    H.emub_estimate_default_opts.argtypes = [ctypes.POINTER(EstimateOpts)]
+    H.emub_estimate_default_opts.restype = None
+    H.emub_sample_scales.argtypes = [_dp, _ci, _ci, _ci, _dp]
+    H.emub_sample_scales.restype = None
+    H.emub_optimization_ranges.argtypes = [_ci, _dp, _ci, _ci, _ci, _dp]
+    H.emub_optimization_ranges.restype = None
+    H.emub_random_init.argtypes = [ctypes.c_ulonglong, _ci, _dp, _ci, _dp]
+    H.emub_random_init.restype = None
+    H.emub_estimate_thetas.argtypes = [_vp, _dp, ctypes.POINTER(EstimateOpts), _dp, _dp, ctypes.POINTER(EstimateStats)]
+    H.emub_estimate_thetas_from.argtypes = [_vp, _dp, _dp, ctypes.POINTER(EstimateOpts), _dp, _dp, ctypes.POINTER(EstimateStats)]
+    _hostlib = H
+    return H
+
+
+def optimization_ranges(kernel, X):
+    """setup_optimization_ranges (optstruct.c:142) on the host: nthetas x 2."""
+    X = _c(X)
+    n, d = X.shape
+    nth = d + 2 if kernel == POWEREXP else 3
+    r = np.empty((nth, 2))
+    host_lib().emub_optimization_ranges(kernel, _P(X), d, n, d, _P(r))
+    return r
+
+
+def random_init(seed, try_index, ranges):
+    ranges = _c(ranges)
+    x = np.empty(ranges.shape[0])
+    host_lib().emub_random_init(seed, try_index, _P(ranges), ranges.shape[0], _P(x))
+    return x
+
+
+def estimate_thetas(model, ranges=None, max_tries=50, nchains=0, seed=1, starts=None):
+    """maxWithMultiMin (maxmultimin.c:47) over the batched GPU evaluator.  Returns (thetas[nthetas], best log
+    likelihood, stats dict).  starts: optional (max_tries x nthetas) explicit start points."""
+    H = host_lib()
+    if ranges is None:
+        ranges = optimization_ranges(model.kernel, model.X)
+    ranges = _c(ranges)
+    o = EstimateOpts()
+    H.emub_estimate_default_opts(ctypes.byref(o))
+    if starts is not None:
+        starts = _c(starts).reshape(-1, model.nthetas)
+        max_tries = starts.shape[0]
+    o.max_tries, o.nchains, o.seed = max_tries, nchains, seed
+    th = np.zeros(model.nthetas)
+    best = ctypes.c_double()
+    st = EstimateStats()
+    rc = H.emub_estimate_thetas_from(model.h, _P(ranges), _P(starts) if starts is not None else None, ctypes.byref(o),
+                                     _P(th), ctypes.byref(best), ctypes.byref(st))
+    if rc not in (OK, EDOM):
+        _check(rc)
+    return th, best.value, dict(rc=rc, evaluations=st.evaluations, batches=st.batches, success_count=st.success_count,
+                                finite_count=st.finite_count)

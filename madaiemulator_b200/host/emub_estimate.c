@@ -1,0 +1,310 @@
+/* emub_estimate.c -- see emub_estimate.h.  Citations are file:line under the reference's src/. */
+#include "emub_estimate.h"
+#include "emub_bfgs.h"
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define SCREWUPVALUE -2000000 /* maxmultimin.h */
+
+void emub_estimate_default_opts(emub_estimate_opts *o)
+{
+	o->max_tries = 50;
+	o->nchains = 0;
+	o->seed = 1;
+	o->step_size = 1.5;
+	o->tol = 0.5;
+	o->eps_abs = 0.1;
+	o->step_max = 30;
+}
+
+/* modelstruct.c:188-213 */
+void emub_sample_scales(const double *X, int ldx, int n, int d, double *scales)
+{
+	for (int i = 0; i < d; i++) {
+		double min_value = (n > 1) ? fabs(X[(size_t)1 * ldx + i] - X[i]) : 1.0;
+		for (int j = 1; j < n - 1; j++) {
+			double value = fabs(X[(size_t)(j + 1) * ldx + i] - X[(size_t)j * ldx + i]);
+			if (value < min_value) min_value = value;
+		}
+		if (min_value < 1.0e-5) min_value = 1.0e-5;
+		scales[i] = min_value;
+	}
+}
+
+/* optstruct.c:142-226 */
+void emub_optimization_ranges(int kernel, const double *X, int ldx, int n, int d, double *ranges)
+{
+	const int nthetas = (kernel == EMUB_POWEREXP) ? d + 2 : 3;
+	double *scales = (double *)malloc(sizeof(double) * (size_t)d);
+	double range_min, range_max;
+	emub_sample_scales(X, ldx, n, d, scales);
+	if (kernel == EMUB_POWEREXP) { range_min = 0.0001; range_max = 5; }
+	else { range_min = 0; range_max = 10.0; }
+	ranges[0] = 0.0001; ranges[1] = range_max; /* amplitude (not optimised, kept for layout) */
+	ranges[2] = -5.0; ranges[3] = -2.0;        /* nugget, optstruct.c:153-154 */
+	for (int i = 2; i < nthetas; i++) {
+		if (kernel == EMUB_POWEREXP) {
+			range_min = 0.5 * log(scales[i - 2]);
+			range_max = log(25 * exp(range_min));
+		} else {
+			range_min = 0.5 * scales[i - 2];
+		}
+		ranges[2 * i] = range_min;
+		ranges[2 * i + 1] = range_max;
+	}
+	free(scales);
+}
+
+static uint64_t splitmix64(uint64_t z)
+{
+	z += 0x9E3779B97F4A7C15ull;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+void emub_random_init(unsigned long long seed, int try_index, const double *ranges, int nthetas, double *x)
+{
+	for (int i = 0; i < nthetas; i++) {
+		uint64_t z = splitmix64(splitmix64(seed) + (uint64_t)try_index * 1024u + (uint64_t)i);
+		double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+		x[i] = u * (ranges[2 * i + 1] - ranges[2 * i]) + ranges[2 * i];
+	}
+}
+
+/* ---- the evaluation front ------------------------------------------------------------------------ */
+enum { REQ_IDLE = 0, REQ_PENDING = 1, REQ_DONE = 2 };
+
+struct front;
+typedef struct {
+	struct front *fr;
+	int id;
+	int state;
+	double *x, *g;        /* request point (nth1), returned gradient */
+	double f, sigma2;
+	int status;
+	/* last evaluated point, so that f(x) followed by df(x) costs one evaluation */
+	double *cx, *cg;
+	double cf, csigma2;
+	int cstatus, cvalid;
+	/* result of this chain's restarts */
+	double best_lhood;
+	double *best_thetas;
+	int success_count, finite_count;
+} chain_t;
+
+typedef struct front {
+	emub_model *model;
+	const emub_estimate_opts *opts;
+	const double *ranges;
+	const double *starts; /* optional max_tries x nthetas explicit start points */
+	int nth, nth1, nchains;
+	pthread_mutex_t mu;
+	pthread_cond_t cv_disp, cv_done;
+	int nactive, npending;
+	chain_t *chains;
+	long long evaluations, batches;
+	int failed;
+} front_t;
+
+static void chain_request(chain_t *c, const double *x)
+{
+	front_t *fr = c->fr;
+	if (c->cvalid && memcmp(c->cx, x, sizeof(double) * (size_t)fr->nth1) == 0) return;
+	pthread_mutex_lock(&fr->mu);
+	memcpy(c->x, x, sizeof(double) * (size_t)fr->nth1);
+	c->state = REQ_PENDING;
+	fr->npending++;
+	if (fr->npending >= fr->nactive) pthread_cond_signal(&fr->cv_disp);
+	while (c->state != REQ_DONE) pthread_cond_wait(&fr->cv_done, &fr->mu);
+	c->state = REQ_IDLE;
+	pthread_mutex_unlock(&fr->mu);
+	memcpy(c->cx, x, sizeof(double) * (size_t)fr->nth1);
+	memcpy(c->cg, c->g, sizeof(double) * (size_t)fr->nth1);
+	c->cf = c->f;
+	c->csigma2 = c->sigma2;
+	c->cstatus = c->status;
+	c->cvalid = 1;
+}
+
+/* evalFnMulti / gradFnMulti / evalFnGradMulti as the optimiser sees them (maxmultimin.c:288, :416, :615) */
+static double cb_f(const double *x, void *ctx)
+{
+	chain_t *c = (chain_t *)ctx;
+	chain_request(c, x);
+	return c->cf;
+}
+static void cb_df(const double *x, void *ctx, double *g)
+{
+	chain_t *c = (chain_t *)ctx;
+	chain_request(c, x);
+	memcpy(g, c->cg, sizeof(double) * (size_t)c->fr->nth1);
+}
+static void cb_fdf(const double *x, void *ctx, double *f, double *g)
+{
+	chain_t *c = (chain_t *)ctx;
+	chain_request(c, x);
+	*f = c->cf;
+	memcpy(g, c->cg, sizeof(double) * (size_t)c->fr->nth1);
+}
+
+/* one restart: doOptimizeMultiMin (maxmultimin.c:633-778) + scoring (maxmultimin.c:98-115) */
+static void run_restart(chain_t *c, int try_index, emub_bfgs *bf)
+{
+	front_t *fr = c->fr;
+	const emub_estimate_opts *o = fr->opts;
+	const int nth = fr->nth, nth1 = fr->nth1;
+	double *x_init = (double *)malloc(sizeof(double) * (size_t)nth);
+	double *x_final = (double *)malloc(sizeof(double) * (size_t)nth1);
+	if (fr->starts) memcpy(x_init, fr->starts + (size_t)try_index * nth, sizeof(double) * (size_t)nth);
+	else emub_random_init(o->seed, try_index, fr->ranges, nth, x_init);
+	emub_bfgs_fn fn = {(size_t)nth1, cb_f, cb_df, cb_fdf, c};
+	int status = emub_bfgs_set(bf, &fn, x_init + 1, o->step_size, o->tol); /* skip the amplitude, :665-668 */
+	int stepcount = 0;
+	do {
+		status = emub_bfgs_iterate(bf);
+		if (status == EMUB_BFGS_ENOPROG && stepcount > 0) break; /* :704-708 */
+		status = emub_bfgs_test_gradient(emub_bfgs_gradient(bf), (size_t)nth1, o->eps_abs);
+		stepcount++;
+	} while (status == EMUB_BFGS_CONTINUE && stepcount < o->step_max);
+	if (status == EMUB_BFGS_OK) c->success_count++;
+	memcpy(x_final, emub_bfgs_x(bf), sizeof(double) * (size_t)nth1);
+	/* sigma re-estimate and score at the final point: one evaluation gives both (:757, :103) */
+	chain_request(c, x_final);
+	const double likelihood = -1.0 * c->cf;
+	if (c->cstatus == 0 && isfinite(likelihood) && isfinite(c->csigma2) && c->csigma2 > 0.0) {
+		c->finite_count++;
+		if (likelihood > c->best_lhood) {
+			c->best_lhood = likelihood;
+			c->best_thetas[0] = log(c->csigma2);
+			memcpy(c->best_thetas + 1, x_final, sizeof(double) * (size_t)nth1);
+		}
+	}
+	free(x_init);
+	free(x_final);
+}
+
+static void *chain_main(void *arg)
+{
+	chain_t *c = (chain_t *)arg;
+	front_t *fr = c->fr;
+	emub_bfgs *bf = emub_bfgs_alloc((size_t)fr->nth1);
+	for (int t = c->id; t < fr->opts->max_tries; t += fr->nchains) {
+		c->cvalid = 0;
+		run_restart(c, t, bf);
+	}
+	emub_bfgs_free(bf);
+	pthread_mutex_lock(&fr->mu);
+	fr->nactive--;
+	pthread_cond_signal(&fr->cv_disp);
+	pthread_mutex_unlock(&fr->mu);
+	return NULL;
+}
+
+int emub_estimate_thetas(emub_model *model, const double *ranges, const emub_estimate_opts *opts_in,
+                         double *thetas_out, double *best_lhood, emub_estimate_stats *stats)
+{
+	return emub_estimate_thetas_from(model, ranges, NULL, opts_in, thetas_out, best_lhood, stats);
+}
+
+int emub_estimate_thetas_from(emub_model *model, const double *ranges, const double *starts,
+                              const emub_estimate_opts *opts_in, double *thetas_out, double *best_lhood,
+                              emub_estimate_stats *stats)
+{
+	if (!model || (!ranges && !starts) || !thetas_out) return EMUB_EINVAL;
+	emub_estimate_opts o;
+	if (opts_in) o = *opts_in; else emub_estimate_default_opts(&o);
+	if (o.max_tries < 1) o.max_tries = 1;
+	int nchains = o.nchains > 0 ? o.nchains : (o.max_tries < 64 ? o.max_tries : 64);
+	if (nchains > o.max_tries) nchains = o.max_tries;
+	front_t fr;
+	memset(&fr, 0, sizeof(fr));
+	fr.model = model; fr.opts = &o; fr.ranges = ranges; fr.starts = starts;
+	fr.nth = emub_model_nthetas(model); fr.nth1 = fr.nth - 1; fr.nchains = nchains;
+	pthread_mutex_init(&fr.mu, NULL);
+	pthread_cond_init(&fr.cv_disp, NULL);
+	pthread_cond_init(&fr.cv_done, NULL);
+	fr.nactive = nchains;
+	fr.chains = (chain_t *)calloc((size_t)nchains, sizeof(chain_t));
+	const size_t vb = sizeof(double) * (size_t)fr.nth;
+	for (int i = 0; i < nchains; i++) {
+		chain_t *c = &fr.chains[i];
+		c->fr = &fr; c->id = i; c->best_lhood = SCREWUPVALUE;
+		c->x = (double *)calloc(1, vb); c->g = (double *)calloc(1, vb);
+		c->cx = (double *)calloc(1, vb); c->cg = (double *)calloc(1, vb);
+		c->best_thetas = (double *)calloc(1, vb);
+	}
+	pthread_t *tids = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nchains);
+	for (int i = 0; i < nchains; i++) pthread_create(&tids[i], NULL, chain_main, &fr.chains[i]);
+
+	/* dispatcher: whenever every live chain is waiting, evaluate the whole front in one GPU call */
+	double *bx = (double *)malloc(sizeof(double) * (size_t)nchains * fr.nth1);
+	double *bg = (double *)malloc(sizeof(double) * (size_t)nchains * fr.nth1);
+	double *bf = (double *)malloc(sizeof(double) * (size_t)nchains);
+	double *bs = (double *)malloc(sizeof(double) * (size_t)nchains);
+	int *bst = (int *)malloc(sizeof(int) * (size_t)nchains);
+	int *who = (int *)malloc(sizeof(int) * (size_t)nchains);
+	int rc = EMUB_OK;
+	pthread_mutex_lock(&fr.mu);
+	for (;;) {
+		while (fr.nactive > 0 && fr.npending < fr.nactive) pthread_cond_wait(&fr.cv_disp, &fr.mu);
+		if (fr.nactive == 0) break;
+		int B = 0;
+		for (int i = 0; i < nchains; i++)
+			if (fr.chains[i].state == REQ_PENDING) {
+				memcpy(bx + (size_t)B * fr.nth1, fr.chains[i].x, sizeof(double) * (size_t)fr.nth1);
+				who[B++] = i;
+			}
+		pthread_mutex_unlock(&fr.mu);
+		int call = emub_loglik_grad_batch(model, bx, B, 1, bf, bg, bs, bst);
+		pthread_mutex_lock(&fr.mu);
+		if (call != EMUB_OK) { rc = call; fr.failed = 1; }
+		fr.evaluations += B;
+		fr.batches++;
+		for (int k = 0; k < B; k++) {
+			chain_t *c = &fr.chains[who[k]];
+			if (call == EMUB_OK) {
+				c->f = bf[k]; c->sigma2 = bs[k]; c->status = bst[k];
+				memcpy(c->g, bg + (size_t)k * fr.nth1, sizeof(double) * (size_t)fr.nth1);
+			} else {
+				c->f = NAN; c->sigma2 = NAN; c->status = EMUB_ECUDA;
+				for (int j = 0; j < fr.nth1; j++) c->g[j] = NAN;
+			}
+			c->state = REQ_DONE;
+		}
+		fr.npending = 0;
+		pthread_cond_broadcast(&fr.cv_done);
+	}
+	pthread_mutex_unlock(&fr.mu);
+	for (int i = 0; i < nchains; i++) pthread_join(tids[i], NULL);
+
+	/* global best over chains, in chain order (deterministic) -- estimate_threaded.c:294-323 */
+	double best = SCREWUPVALUE;
+	int succ = 0, fin = 0;
+	for (int i = 0; i < nchains; i++) {
+		chain_t *c = &fr.chains[i];
+		succ += c->success_count;
+		fin += c->finite_count;
+		if (c->best_lhood > best) {
+			best = c->best_lhood;
+			memcpy(thetas_out, c->best_thetas, vb);
+		}
+	}
+	if (best_lhood) *best_lhood = best;
+	if (stats) { stats->evaluations = fr.evaluations; stats->batches = fr.batches; stats->success_count = succ; stats->finite_count = fin; }
+	for (int i = 0; i < nchains; i++) {
+		chain_t *c = &fr.chains[i];
+		free(c->x); free(c->g); free(c->cx); free(c->cg); free(c->best_thetas);
+	}
+	free(fr.chains); free(tids); free(bx); free(bg); free(bf); free(bs); free(bst); free(who);
+	pthread_mutex_destroy(&fr.mu); pthread_cond_destroy(&fr.cv_disp); pthread_cond_destroy(&fr.cv_done);
+	if (rc != EMUB_OK) return rc;
+	if (best == SCREWUPVALUE) {
+		for (int i = 0; i < fr.nth; i++) thetas_out[i] = 0.0;
+		return EMUB_EDOM;
+	}
+	return EMUB_OK;
+}

@@ -1,0 +1,66 @@
+/*
+ * emub_estimate.h -- host-side (plain C) hyper-parameter estimation over the batched GPU evaluator.
+ *
+ * Replaces the reference's restart machinery for the hot path: estimate_thetas_threaded
+ * (src/libEmu/estimate_threaded.c:78) -> maxWithMultiMin (src/libEmu/maxmultimin.c:47) ->
+ * doOptimizeMultiMin (:633).  The optimiser stays on the host exactly as in the reference -- one BFGS
+ * chain per pthread, the reference's own parallel model (estimate_threaded.c:172) -- but no chain ever
+ * evaluates a likelihood itself: every evalFnMulti / gradFnMulti request is parked in a queue, and when
+ * all live chains are waiting the dispatcher issues ONE emub_loglik_grad_batch call for the whole front
+ * (include/emu_b200.h).  Results do not depend on thread timing: start points come from a counter-based
+ * generator keyed by (seed, try index) and the batched evaluator is bit-wise independent of the batch
+ * composition.
+ */
+#ifndef EMUB_ESTIMATE_H
+#define EMUB_ESTIMATE_H
+#include "../../include/emu_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+	int max_tries;            /* random restarts; reference: 50 per job x ncpus jobs (estimate_threaded.c:101,113) */
+	int nchains;              /* concurrent BFGS chains = width of the evaluation front (0: min(max_tries, 64)) */
+	unsigned long long seed;  /* reference: /dev/urandom (useful.c:49); here explicit and reproducible */
+	double step_size;         /* 1.5   maxmultimin.c:644 */
+	double tol;               /* 0.5   maxmultimin.c:645 */
+	double eps_abs;           /* 0.1   maxmultimin.c:650 */
+	int step_max;             /* 30    maxmultimin.c:641 */
+} emub_estimate_opts;
+
+typedef struct {
+	long long evaluations;    /* likelihood(+gradient) points evaluated on the GPU */
+	long long batches;        /* emub_loglik_grad_batch calls */
+	int success_count;        /* chains that stopped on |g| < eps_abs (maxmultimin.c:91-92) */
+	int finite_count;         /* restarts with a finite final likelihood (maxmultimin.c:110) */
+} emub_estimate_stats;
+
+void emub_estimate_default_opts(emub_estimate_opts *o);
+
+/* sample scales (modelstruct.c:188-213) and optimiser search ranges (optstruct.c:142-226, use_data_scales = 1,
+ * no fixed nugget); ranges is nthetas x 2 row-major */
+void emub_sample_scales(const double *X, int ldx, int n, int d, double *scales);
+void emub_optimization_ranges(int kernel, const double *X, int ldx, int n, int d, double *ranges);
+
+/* start point of restart `try_index`: uniform in ranges (set_random_init_value, maxmultimin.c:789-804) */
+void emub_random_init(unsigned long long seed, int try_index, const double *ranges, int nthetas, double *x);
+
+/*
+ * maxWithMultiMin over the batched evaluator.  thetas_out (nthetas): best point, thetas_out[0] =
+ * log(sigma^2) re-estimated at the optimum (maxmultimin.c:757-769).  best_lhood: its log-likelihood
+ * (maxmultimin.c:103).  Returns EMUB_OK, or EMUB_EDOM when no restart produced a finite likelihood
+ * ("maximisation didn't work at all", maxmultimin.c:121-123).
+ */
+int emub_estimate_thetas(emub_model *model, const double *ranges, const emub_estimate_opts *opts,
+                         double *thetas_out, double *best_lhood, emub_estimate_stats *stats);
+
+/* same, but restart t starts from starts[t * nthetas ..] (max_tries rows; entry 0 of each row, the amplitude, is
+ * ignored as in maxmultimin.c:665-668) instead of a random point; ranges may then be NULL */
+int emub_estimate_thetas_from(emub_model *model, const double *ranges, const double *starts,
+                              const emub_estimate_opts *opts, double *thetas_out, double *best_lhood,
+                              emub_estimate_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

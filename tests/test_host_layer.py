@@ -1,0 +1,72 @@
+"""Host C layer (madaiemulator_b200/host): ranges and start points on CPU; the batched restart driver on the GPU
+against the reference's own maxWithMultiMin (oracle/_ref)."""
+import numpy as np
+import pytest
+
+from madaiemulator_b200 import datasets as ds
+from tests.helpers import load_golden
+
+
+def test_ranges_match_reference_goldens():
+    from madaiemulator_b200 import engine
+    for name in ("uni-simple-o1", "uni-2d-o0", "multi-simple-pc0-o0", "synthetic-n256-d10-o1", "uni-simple-m32", "multi-simple-m52"):
+        c = load_golden(name)
+        r = engine.optimization_ranges(c["kernel"], c["X"])
+        assert np.array_equal(r.ravel(), c["ranges"].ravel()), name
+
+
+def test_random_init_inside_ranges_and_reproducible():
+    from madaiemulator_b200 import engine
+    X = ds.synthetic_design(64, 3)
+    r = engine.optimization_ranges(1, X)
+    a = np.stack([engine.random_init(7, t, r) for t in range(40)])
+    b = np.stack([engine.random_init(7, t, r) for t in range(40)])
+    assert np.array_equal(a, b)
+    assert np.all(a >= r[:, 0]) and np.all(a <= r[:, 1])
+    assert len(np.unique(a[:, 1])) == 40
+    assert not np.array_equal(a, np.stack([engine.random_init(8, t, r) for t in range(40)]))
+
+
+def test_host_library_exports():
+    from madaiemulator_b200 import engine
+    H = engine.host_lib()
+    for s in engine.HOST_SYMBOLS:
+        assert hasattr(H, s)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,tries", [("uni-simple-o1", 24), ("uni-2d-o0", 8), ("multi-simple-pc0-o0", 16)])
+def test_estimate_thetas_reaches_reference_likelihood(name, tries):
+    """north_star: end-to-end estimate_thetas must reach a log-likelihood no worse than the reference's.  The
+    reference side is its own maxWithMultiMin (compiled from the reference sources) with the same number of
+    restarts; both sides are scored with the oracle's likelihood at their returned thetas."""
+    from madaiemulator_b200 import engine
+    from oracle.pyoracle import PortOracle, RefOracle, ref_available
+    c = load_golden(name)
+    ctx = engine.Context(0)
+    m = engine.Model(ctx, c["X"], c["y"], c["kernel"], c["order"], max_slots=32)
+    th, best, st = engine.estimate_thetas(m, max_tries=tries, nchains=min(tries, 32), seed=11)
+    assert st["rc"] == 0 and st["finite_count"] > 0
+    assert st["batches"] < st["evaluations"]  # the front really is batched
+    po = PortOracle(c["X"], c["y"], c["kernel"], c["order"])
+    ours = -po.loglik_grad(th[1:], want_grad=False)["negL"]
+    assert abs(ours - best) <= 1e-9 * max(1.0, abs(best))
+    # theta_0 is the log of sigma^2 at the optimum (maxmultimin.c:757-769).  The optimum sits at long length
+    # scales where cond(C) is ~1e8 and sigma^2 = y.C^-1 (y - H beta) / n is a cancellation, so two correct FP64
+    # evaluations agree to ~cond * eps rather than 1e-9 (the fixed-theta parity tests cover the 1e-9 bar).
+    assert abs(th[0] - np.log(po.loglik_grad(th[1:], want_grad=False)["sigma2"])) < 1e-6
+    # same seed -> same answer, whatever the thread timing
+    th2, best2, _ = engine.estimate_thetas(m, max_tries=tries, nchains=min(tries, 32), seed=11)
+    assert np.array_equal(th, th2) and best == best2
+    if ref_available():
+        # like for like: the reference's own maxWithMultiMin draws its start points from its RNG stream; give the
+        # engine exactly those points (both sides then run the same BFGS on 1e-9-equal objective values)
+        ref = RefOracle(c["X"], c["y"], c["kernel"], c["order"])
+        starts = ref.random_inits(11, tries)
+        ref_best, ref_th = ref.max_with_multimin(tries, 11)
+        ref_scored = -po.loglik_grad(ref_th[1:], want_grad=False)["negL"]
+        th3, best3, st3 = engine.estimate_thetas(m, starts=starts, nchains=min(tries, 32))
+        ours3 = -po.loglik_grad(th3[1:], want_grad=False)["negL"]
+        assert ours3 >= ref_scored - 1e-6 * max(1.0, abs(ref_scored)), (ours3, ref_scored)
+    m.close()
+    ctx.close()
