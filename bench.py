@@ -56,20 +56,6 @@ def theta_batch(ranges, B, seed):
     return lo[None, :] + u * (hi - lo)[None, :]
 
 
-def powerexp_ranges(X):
-    """optstruct.c:142-226 with use_data_scales=1 (host logic; the sample scales follow modelstruct.c:188-213)."""
-    n, d = X.shape
-    gaps = np.abs(np.diff(X, axis=0)).min(axis=0)
-    gaps = np.maximum(gaps, 1.0e-5)
-    r = np.zeros((d + 2, 2))
-    r[0] = (0.0001, 5.0)
-    r[1] = (-5.0, -2.0)
-    lo = 0.5 * np.log(gaps)
-    r[2:, 0] = lo
-    r[2:, 1] = np.log(25.0 * np.exp(lo))
-    return r
-
-
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -220,7 +206,7 @@ def main():
 
     X = ds.synthetic_design(N_MODEL, D_MODEL)
     y = ds.synthetic_response(X)
-    ranges = powerexp_ranges(X)
+    ranges = engine.optimization_ranges(engine.POWEREXP, X)  # host C: optstruct.c:142-226
     B = args.batch
     thetas = theta_batch(ranges, B, ds.SEED + 17 + rank)
     nth1 = D_MODEL + 1
@@ -236,13 +222,12 @@ def main():
     def step_dev():
         model.loglik_grad_batch_dev(d_thetas.data_ptr(), B, True, d_out.data_ptr())
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # samples through warm-up and the timed region (nvidia-smi takes ~1 s to start reporting)
     for _ in range(max(3, args.warmup)):
         step_dev()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -113,6 +113,8 @@ long long emub_launch_count(emub_ctx *ctx);
 /* copy an internal n x n matrix of slot b of the last batch to the host: which = 0 Cinv (lower
  * triangle + diagonal blocks valid), 1 W = L^-1 (lower) */
 int emub_debug_fetch(emub_model *m, int b, int which, double *out, int ldo);
+/* the device exp used by the covariance / gradient kernels (x <= 0), for accuracy tests */
+int emub_debug_exp(emub_ctx *ctx, const double *x, int n, double *out);
 /* factor only: runs covariance + Cholesky at theta-less-amp and returns L (lower, n x n) */
 int emub_debug_cholesky(emub_model *m, const double *theta_less_amp, double *L, int ldl, double *logdet);
 

@@ -656,6 +656,24 @@ extern "C" int emub_debug_fetch(emub_model *m, int b, int which, double *out, in
 	return EMUB_OK;
 }
 
+extern "C" int emub_debug_exp(emub_ctx *c, const double *x, int n, double *out)
+{
+	if (!c || !x || !out || n < 1) return set_err(EMUB_EINVAL, "emub_debug_exp: bad argument%s");
+	CUDA_TRY(cudaSetDevice(c->device));
+	double *dx = nullptr, *dout = nullptr;
+	CUDA_TRY(cudaMalloc(&dx, sizeof(double) * n));
+	CUDA_TRY(cudaMalloc(&dout, sizeof(double) * n));
+	CUDA_TRY(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+	{
+		LaunchScope ls(c, EMUB_K_SMALL, 0, c->streams[0]);
+		k_debug_exp<<<(n + 255) / 256, 256, 0, c->streams[0]>>>(dx, n, dout);
+	}
+	CUDA_TRY(cudaStreamSynchronize(c->streams[0]));
+	CUDA_TRY(cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
+	cudaFree(dx); cudaFree(dout);
+	return EMUB_OK;
+}
+
 extern "C" int emub_debug_cholesky(emub_model *m, const double *theta_less_amp, double *L, int ldl, double *logdet)
 {
 	if (!m || !theta_less_amp || !L || ldl < m->n) return set_err(EMUB_EINVAL, "emub_debug_cholesky: bad argument%s");

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include "emub_gemm.cuh"
+#include "emub_exp.cuh"
 
 namespace emub {
 
@@ -54,19 +55,21 @@ __global__ void k_theta_prep(const double *__restrict__ thetas, int B, int nth_i
 // ---- covariance pair functions (literal operation order of the reference) -------------------------
 template <int KERNEL>
 __device__ __forceinline__ double cov_pair(const double *xi, int si, const double *xj, int sj, int d,
-                                           const double *__restrict__ c)
+                                           const double *__restrict__ c, const double *__restrict__ tab)
 {
 	if (KERNEL == 1) {
 		// emulator.c:101-152
+		// exponent += (-1/2) dist^2 / l_k^2 (scaling by 1/2 is exact, so this is the literal sum up to the
+		// reciprocal of deviation D-5); "all |dist| < 1e-10" is tracked as one predicate
 		double e = 0.0;
-		int cnt = 0;
+		bool same = true;
 		for (int k = 0; k < d; k++) {
-			double dist = fabs(xi[k * si] - xj[k * sj]);
+			const double dist = fabs(xi[k * si] - xj[k * sj]);
 			e += ((-0.5 * dist) * dist) * c[4 + k];
-			cnt += (dist < 0.0000000001);
+			same = same && (dist < 0.0000000001);
 		}
-		double v = exp(e) * c[0];
-		if (cnt == d) v += c[1];
+		double v = exp_neg(e, tab) * c[0];
+		if (same) v += c[1];
 		return v;
 	} else {
 		// emulator.c:344-386 (Matern 3/2), :438-480 (Matern 5/2)
@@ -81,12 +84,12 @@ __device__ __forceinline__ double cov_pair(const double *xi, int si, const doubl
 		double v;
 		if (KERNEL == 2) {
 			const double root3 = 1.732050808;
-			if (dist > 0.0) v = c[0] * (1 + root3 * (dist / c[2])) * exp(-root3 * (dist / c[2]));
+			if (dist > 0.0) v = c[0] * (1 + root3 * (dist / c[2])) * exp_neg(-root3 * (dist / c[2]), tab);
 			else v = c[0];
 		} else {
 			const double root5 = 2.236067978;
 			double dr = dist / c[2];
-			if (dist > 0.0) v = c[0] * (1 + root5 * dr + (5.0 / 3.0) * dr * dr) * exp(-root5 * dr);
+			if (dist > 0.0) v = c[0] * (1 + root5 * dr + (5.0 / 3.0) * dr * dr) * exp_neg(-root5 * dr, tab);
 			else v = c[0];
 		}
 		if (cnt == d) v += c[1];
@@ -109,6 +112,8 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 	double *sXi = sm;            // [d][64]
 	double *sXj = sm + d * CT;   // [d][64]
 	__shared__ double sc[CONST_STRIDE];
+	__shared__ double stab[64];
+	exp_table_load(stab);
 	const int tid = threadIdx.x;
 	const double *cg = consts + b * const_stride;
 	for (int i = tid; i < 4 + 3 * d; i += 256) sc[i] = cg[i];
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 			const int lj = tx + 16 * c, gj = j0 + lj;
 			double v;
 			if (gi < n && gj < ncols) {
-				v = cov_pair<KERNEL>(sXi + li, CT, sXj + lj, CT, d, sc);
+				v = cov_pair<KERNEL>(sXi + li, CT, sXj + lj, CT, d, sc, stab);
 				if (CROSS && v < 1E-10) v = 0.0;
 			} else {
 				v = (!CROSS && gi == gj) ? 1.0 : 0.0;
@@ -574,6 +579,8 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 	double *sAi = sm + 2 * d * CT, *sAj = sAi + CT;
 	__shared__ double sc[CONST_STRIDE];
 	__shared__ double red[8][MAXD];
+	__shared__ double stab[64];
+	exp_table_load(stab);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const double *cg = consts + (size_t)b * CONST_STRIDE;
 	for (int i = tid; i < 4 + 3 * d; i += 256) sc[i] = cg[i];
@@ -613,7 +620,7 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 				for (int c = 0; c < 4; c++) {
 					const double dl = xi - sXj[k * CT + tx + 16 * c];
 					const double q = dl * dl;
-					s += w[r][c] * (q * exp(-ak * q));
+					s += w[r][c] * (q * exp_neg(-ak * q, stab));
 				}
 			}
 #pragma unroll
@@ -634,7 +641,7 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 					r2 += dl * dl;
 				}
 				const double t = root * (sqrt(r2) / rho);
-				const double f = (KERNEL == 2) ? t * t * exp(-t) : (t * t / 3.0) * (1.0 + t) * exp(-t);
+				const double f = (KERNEL == 2) ? t * t * exp_neg(-t, stab) : (t * t / 3.0) * (1.0 + t) * exp_neg(-t, stab);
 				s += w[r][c] * f;
 			}
 #pragma unroll
@@ -695,6 +702,16 @@ __global__ void __launch_bounds__(256) k_grad_final(const double *__restrict__ p
 		r[7] = aa;
 		r[RES_GRAD] = failed ? nan("") : -1.0 * (-0.5 * nug * tr + 0.5 * nug * aa);
 	}
+}
+
+// test hook: the device exp on an array
+__global__ void k_debug_exp(const double *__restrict__ x, int n, double *__restrict__ out)
+{
+	__shared__ double stab[64];
+	exp_table_load(stab);
+	__syncthreads();
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = exp_neg(x[i], stab);
 }
 
 // pack results for the device-pointer API: out[b] = (negL, sigma2, status, logdet, grad[nth1])

@@ -34,7 +34,7 @@ SYMBOLS = [
     "emub_ctx_synchronize", "emub_loglik_extras", "emub_emulator_create", "emub_emulator_destroy",
     "emub_emulator_beta", "emub_predict_batch", "emub_predict_batch_dev", "emub_profile_enable",
     "emub_profile_reset", "emub_profile_read", "emub_profile_name", "emub_launch_count", "emub_debug_fetch",
-    "emub_debug_cholesky",
+    "emub_debug_cholesky", "emub_debug_exp",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
     L.emub_launch_count.restype = _ll
     L.emub_debug_fetch.argtypes = [_vp, _ci, _ci, _dp, _ci]
     L.emub_debug_cholesky.argtypes = [_vp, _dp, _dp, _ci, _dp]
+    L.emub_debug_exp.argtypes = [_vp, _dp, _ci, _dp]
     _lib = L
     return L
 
@@ -130,6 +131,12 @@ class Context:
 
     def synchronize(self):
         _check(self.L.emub_ctx_synchronize(self.h))
+
+    def debug_exp(self, x):
+        x = _c(x).ravel()
+        out = np.empty_like(x)
+        _check(self.L.emub_debug_exp(self.h, _P(x), x.size, _P(out)))
+        return out
 
     def launch_count(self):
         return int(self.L.emub_launch_count(self.h))

@@ -73,7 +73,16 @@ def test_golden_fixture(ctx, name):
         # regression basis, e.g. uni-2d order 2): judged relative to its constituent |y.C^-1 y| / n
         assert abs(r["sigma2"] - c["sigma2"]) < TOL * _sigma2_scale(c["X"], c["y"], c["kernel"], c["order"], c["theta_less_amp"])
         assert relerr(r["beta"], c["beta"], 1e-6) < TOL
-        assert _grad_err(r["grad"], c["grad"]) < TOL
+        s2scale = _sigma2_scale(c["X"], c["y"], c["kernel"], c["order"], c["theta_less_amp"])
+        if abs(c["sigma2"]) > 1e-9 * s2scale:
+            assert _grad_err(r["grad"], c["grad"]) < TOL
+        else:
+            # degenerate fixture (uni-2d order 2: y lies in the span of the regression basis): sigma2 is rounding
+            # noise of either sign, and the length components -exp(log(sigma2)) * (...) (maxmultimin.c:514,531) are
+            # noise or NaN in the reference too.  Only the nugget component is defined.
+            assert relerr(r["grad"][0], c["grad"][0]) < TOL
+            rest = r["grad"][1:]
+            assert np.all(np.isnan(rest) | (np.abs(rest) < 1e-6 * abs(c["grad"][0])))
         if np.isfinite(c["negL_literal"]):
             # deviation D-1: identical to the reference's literal product determinant where that is finite
             assert relerr(r["negL"], c["negL_literal"]) < TOL
@@ -236,3 +245,17 @@ def test_large_properties(ctx):
     assert np.all(var > -1e-9) and np.all(var < 0.1 * np.exp(full[0]) + 1e-6)
     e.close()
     m.close()
+
+
+def test_device_exp(ctx):
+    """The table-driven exp of the covariance / gradient kernels: < 2 ulp on (-708, 0], 0 below."""
+    import mpmath as mp
+    rng = np.random.default_rng(0)
+    x = np.concatenate([-rng.uniform(0, 700, 20000), -rng.uniform(0, 1, 5000), -10.0 ** rng.uniform(-20, 0, 2000),
+                        np.array([0.0, -0.0, -707.9, -708.5, -1e3, -1e6, -1e300])])
+    got = ctx.debug_exp(x)
+    ref = np.array([float(mp.exp(mp.mpf(float(v)))) for v in x])
+    live = x >= -708.0
+    ulps = np.abs(got[live] - ref[live]) / np.spacing(ref[live])
+    assert ulps.max() < 2.0
+    assert np.all(got[~live] == 0.0)
