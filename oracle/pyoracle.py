@@ -159,15 +159,20 @@ def backproject(training_mean, evecs, evals, mean_pca, var_pca):
     return mo, vo
 
 
+def dropin_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libemu_dropin.so"))
+
+
 class RefOracle:
     """The reference's own sources (oracle/_ref/libemu_ref.so)."""
 
     _lib = None
+    _libname = "libemu_ref.so"
 
     @classmethod
     def lib(cls):
-        if cls._lib is None:
-            path = os.path.join(_HERE, "_ref", "libemu_ref.so")
+        if cls.__dict__.get("_lib") is None:
+            path = os.path.join(_HERE, "_ref", cls._libname)
             if not os.path.exists(path):
                 build(ref=True)
             L = ctypes.CDLL(path)
@@ -205,7 +210,7 @@ class RefOracle:
             L.ref_time_emulate.argtypes = [_vp, _dp, _ci, _ci, _dp, _dp]
             L.ref_ncpus.restype = _ci
             cls._lib = L
-        return cls._lib
+        return cls.__dict__["_lib"]
 
     def __init__(self, X, y, kernel=POWEREXP, order=0):
         self.L = self.lib()
@@ -322,3 +327,17 @@ def time_ref_emulate(X, y, thetas, pts, kernel=POWEREXP, order=0, nthreads=1):
     mean, var = np.empty(m), np.empty(m)
     t = RefOracle.lib().ref_time_emulate(e.h, _P(pts), m, nthreads, _P(mean), _P(var))
     return t, mean, var
+
+
+class DropinOracle(RefOracle):
+    """The reference's own sources with the hot-path libEmu symbols replaced by integration/libemu_glue.c, i.e. the
+    reference running on top of the CUDA engine (oracle/_ref/libemu_dropin.so; needs a B200)."""
+
+    _lib = None
+    _libname = "libemu_dropin.so"
+
+    @classmethod
+    def reset(cls):
+        L = cls.lib()
+        L.libemu_glue_reset.restype = None
+        L.libemu_glue_reset()

@@ -1,0 +1,59 @@
+"""GPU: the drop-in boundary end to end.  oracle/_ref/libemu_dropin.so is the reference's own, unmodified C
+(maxWithMultiMin, doOptimizeMultiMin, modelstruct/optstruct set-up, ...) linked with integration/libemu_glue.c,
+which defines evalFnMulti / gradFnMulti / evalFnGradMulti / estimateSigmaFull / alloc_emulator_struct /
+emulate_point / makeCovMatrix_fnptr with the reference's signatures and forwards them to the CUDA engine.  The
+same driver calls on the pure-CPU reference build (libemu_ref.so) are the expected values."""
+import numpy as np
+import pytest
+
+from madaiemulator_b200 import datasets as ds
+from tests.helpers import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracles():
+    from oracle import pyoracle as po
+    if not (po.ref_available() and po.dropin_available()):
+        pytest.skip("oracle/_ref drop-in build not present")
+    yield po
+    po.DropinOracle.reset()
+
+
+@pytest.mark.parametrize("name", ["uni-simple-o1", "multi-simple-pc0-o1", "synthetic-n256-d10-o1"])
+def test_reference_symbols_run_on_the_engine(oracles, name):
+    po = oracles
+    c = load_golden(name)
+    ref = po.RefOracle(c["X"], c["y"], c["kernel"], c["order"])
+    dro = po.DropinOracle(c["X"], c["y"], c["kernel"], c["order"])
+    th = c["theta_less_amp"]
+    # evalFnMulti / gradFnMulti through the reference's own driver
+    assert relerr(dro.eval(th), ref.eval(th)) < 1e-9
+    g_ref, g_dro = ref.grad(th), dro.grad(th)
+    scale = np.maximum(np.abs(g_ref), 1e-3 * np.max(np.abs(g_ref)))
+    assert np.max(np.abs(g_dro - g_ref) / scale) < 1e-9
+    assert relerr(dro.sigma_full(th), ref.sigma_full(th)) < 1e-9
+    # makeCovMatrix_fnptr
+    assert relerr(dro.cov_matrix(c["theta_full"]), ref.cov_matrix(c["theta_full"]), 1e-300) < 1e-9
+    # alloc_emulator_struct + emulate_point
+    m1, v1 = ref.emulator(c["theta_full"]).emulate(c["pts"][:40])
+    e = dro.emulator(c["theta_full"])
+    m2, v2 = e.emulate(c["pts"][:40])
+    assert relerr(m2, m1, 1e-3) < 1e-9
+    assert np.max(np.abs(v2 - v1)) < 1e-9 * max(1.0, float(c["kappa"]))
+    assert relerr(e.beta(), c["emu_beta"], 1e-6) < 1e-9
+    del e
+
+
+def test_reference_restart_driver_on_the_engine(oracles):
+    """The reference's unmodified maxWithMultiMin / doOptimizeMultiMin, every likelihood call served by the GPU:
+    same seed, same start points -> the same optimum as the all-CPU reference."""
+    po = oracles
+    c = load_golden("uni-simple-o1")
+    ref = po.RefOracle(c["X"], c["y"], c["kernel"], c["order"])
+    dro = po.DropinOracle(c["X"], c["y"], c["kernel"], c["order"])
+    best_ref, th_ref = ref.max_with_multimin(6, 5)
+    best_dro, th_dro = dro.max_with_multimin(6, 5)
+    assert abs(best_dro - best_ref) < 1e-6 * max(1.0, abs(best_ref))
+    assert np.max(np.abs(th_dro - th_ref)) < 1e-4
