@@ -199,7 +199,7 @@ static void build_factor(emub_model *m, int lo, int hi, std::vector<GemmTask> &t
 	auto emit = [&](int type, std::vector<GemmTask> &t) {
 		std::stable_sort(t.begin(), t.end(), by_k);
 		FactorStep st{type, (int)tasks.size(), (int)t.size(), 0, 0.0};
-		for (auto &x : t) { tasks.push_back(x); st.flops += ((x.aux & TASK_LOWER) ? 0.75 : 1.0) * 2.0 * TB * TB * (double)x.klen; }
+		for (auto &x : t) { tasks.push_back(x); st.flops += task_flops(x); }
 		m->steps.push_back(st);
 	};
 	if (hi - lo == 1) {
@@ -211,7 +211,7 @@ static void build_factor(emub_model *m, int lo, int hi, std::vector<GemmTask> &t
 	std::vector<GemmTask> t;
 	// L(i,j) = sum_{k in [lo, j]} A(i,k) W(j,k)^T          A = bufA KMAJOR, B = bufW KMAJOR -> bufT
 	for (int i = mid; i < hi; i++)
-		for (int j = lo; j < mid; j++) t.push_back({off(i, lo), off(j, lo), off(i, j), (j - lo + 1) * TB, 0});
+		for (int j = lo; j < mid; j++) t.push_back({off(i, lo), off(j, lo), off(i, j), (j - lo + 1) * TB, TASK_TRIM_END_SC0});
 	emit(STEP_TRSM, t);
 	t.clear();
 	// A(i,j) -= sum_{k in [lo, mid)} L(i,k) L(j,k)^T      A, B = bufT KMAJOR -> bufA
@@ -222,12 +222,12 @@ static void build_factor(emub_model *m, int lo, int hi, std::vector<GemmTask> &t
 	t.clear();
 	// T(i,j) = sum_{k in [j, mid)} L(i,k) W(k,j)           A = bufT KMAJOR, B = bufW RMAJOR -> bufA
 	for (int i = mid; i < hi; i++)
-		for (int j = lo; j < mid; j++) t.push_back({off(i, j), off(j, j), off(i, j), (mid - j) * TB, 0});
+		for (int j = lo; j < mid; j++) t.push_back({off(i, j), off(j, j), off(i, j), (mid - j) * TB, TASK_TRIM_BEGIN_SC1});
 	emit(STEP_TMUL, t);
 	t.clear();
 	// W(i,j) = - sum_{k in [mid, i]} W(i,k) T(k,j)         A = bufW KMAJOR, B = bufA RMAJOR -> bufW
 	for (int i = mid; i < hi; i++)
-		for (int j = lo; j < mid; j++) t.push_back({off(i, mid), off(mid, j), off(i, j), (i + 1 - mid) * TB, 0});
+		for (int j = lo; j < mid; j++) t.push_back({off(i, mid), off(mid, j), off(i, j), (i + 1 - mid) * TB, TASK_TRIM_END_SR0});
 	emit(STEP_WMUL, t);
 }
 
@@ -242,8 +242,8 @@ static void build_schedules(emub_model *m, std::vector<GemmTask> &tasks)
 	m->lauum_flops = 0;
 	for (int i = 0; i < nb; i++)
 		for (int j = 0; j <= i; j++) {
-			tasks.push_back({off(i, i), off(i, j), off(i, j), (nb - i) * TB, (i == j) ? TASK_LOWER : 0});
-			m->lauum_flops += ((i == j) ? 0.75 : 1.0) * 2.0 * TB * TB * (double)(nb - i) * TB;
+			tasks.push_back({off(i, i), off(i, j), off(i, j), (nb - i) * TB, TASK_TRIM_BEGIN_SR1 | ((i == j) ? TASK_LOWER : 0)});
+			m->lauum_flops += task_flops(tasks.back());
 		}
 	m->lauum_cnt = (int)tasks.size() - m->lauum_off;
 }
@@ -757,7 +757,7 @@ extern "C" int emub_emulator_create(emub_model *m, const double *thetas, emub_em
 	CUDA_TRY(cudaMallocHost(&e->hOut, sizeof(double) * 2 * mqc));
 	// V = W K, one task per row block (longest K first); the batch dimension walks the query blocks
 	std::vector<GemmTask> tasks;
-	for (int i = m->nblk - 1; i >= 0; i--) tasks.push_back({(long long)i * TB * m->npad, 0, 0, (i + 1) * TB, i});
+	for (int i = m->nblk - 1; i >= 0; i--) tasks.push_back({(long long)i * TB * m->npad, 0, 0, (i + 1) * TB, i | TASK_TRIM_END_SR0});
 	CUDA_TRY(cudaMalloc(&e->dTasks, tasks.size() * sizeof(GemmTask)));
 	CUDA_TRY(cudaMemcpyAsync(e->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
@@ -793,7 +793,7 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 	launch_kcross(m, st, e->consts, dQ, mq, mq_pad, e->dK, ldk);
 	const int nqb = mq_pad / TB;
 	// |W k|^2 partials: tile (row block i, query block qb)
-	launch_gemm<KMAJOR, RMAJOR, EPI_COLSUMSQ>(c, EMUB_K_GEMM_PRED, (double)m->npad * (m->npad + TB) * TB, st, e->dTasks, m->nblk, nqb,
+	launch_gemm<KMAJOR, RMAJOR, EPI_COLSUMSQ>(c, EMUB_K_GEMM_PRED, (double)m->npad * (m->npad + TB / 2) * TB, st, e->dTasks, m->nblk, nqb,
 	                                          e->W, 0, m->npad, e->dK, TB, ldk, e->dVsq, TB, ldk, 1.0);
 	{
 		const int nchunk_cols = (m->p + 1 + 7) / 8;

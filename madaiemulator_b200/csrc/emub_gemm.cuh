@@ -174,6 +174,30 @@ __device__ __forceinline__ void gemm_mainloop(const double *__restrict__ gA, con
 // grid: (ntasks * SUBS, batch).  TASK_LOWER in task.aux (EPI_STORE / EPI_SUB): the tile is a diagonal tile of a
 // symmetric / triangular result, sub-tiles strictly above the diagonal are skipped.
 constexpr int TASK_LOWER = 1 << 30;
+// K-range trimming at sub-tile granularity for products against a triangular diagonal block (valid for 64 x 64
+// sub-tiles): the first / last 64 k of the range multiply structural zeros for one half of the sub-tiles.
+constexpr int TASK_TRIM_END_SC0 = 1 << 29;    // B's last k-block is lower triangular in (n, k): columns n < 64 need k < 64
+constexpr int TASK_TRIM_BEGIN_SC1 = 1 << 28;  // B's first k-block is upper triangular in (n, k): columns n >= 64 need k >= 64
+constexpr int TASK_TRIM_END_SR0 = 1 << 27;    // same for A and the rows m
+constexpr int TASK_TRIM_BEGIN_SR1 = 1 << 26;
+constexpr int TASK_FLAGS = TASK_LOWER | TASK_TRIM_END_SC0 | TASK_TRIM_BEGIN_SC1 | TASK_TRIM_END_SR0 | TASK_TRIM_BEGIN_SR1;
+
+// executed flops of one task under the default 64 x 64 sub-tiling (host side bookkeeping)
+inline double task_flops(const GemmTask &t)
+{
+	double f = 0.0;
+	for (int sr = 0; sr < 2; sr++)
+		for (int sc = 0; sc < 2; sc++) {
+			if ((t.aux & TASK_LOWER) && sc > sr) continue;
+			int k = t.klen;
+			if ((t.aux & TASK_TRIM_END_SC0) && sc == 0) k -= 64;
+			if ((t.aux & TASK_TRIM_BEGIN_SC1) && sc == 1) k -= 64;
+			if ((t.aux & TASK_TRIM_END_SR0) && sr == 0) k -= 64;
+			if ((t.aux & TASK_TRIM_BEGIN_SR1) && sr == 1) k -= 64;
+			f += 2.0 * 64 * 64 * (double)k;
+		}
+	return f;
+}
 
 template <int AL, int BL, int EPI, class Cfg = DefaultCfg>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) k_gemm(GemmArgs p)
@@ -187,6 +211,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) k_gemm(GemmArgs p)
 	const int b = blockIdx.y;
 	const double *gA = p.A + b * p.strideA + task.a_off + ((AL == KMAJOR) ? (long long)sr * Cfg::BM * p.lda : (long long)sr * Cfg::BM);
 	const double *gB = p.B + b * p.strideB + task.b_off + ((BL == KMAJOR) ? (long long)sc * Cfg::BN * p.ldb : (long long)sc * Cfg::BN);
+	int klen = task.klen;
+	if (Cfg::BM == 64 && Cfg::BN == 64) {
+		const bool trim_end = ((task.aux & TASK_TRIM_END_SC0) && sc == 0) || ((task.aux & TASK_TRIM_END_SR0) && sr == 0);
+		const bool trim_begin = ((task.aux & TASK_TRIM_BEGIN_SC1) && sc == 1) || ((task.aux & TASK_TRIM_BEGIN_SR1) && sr == 1);
+		if (trim_end) klen -= 64;
+		if (trim_begin) {
+			klen -= 64;
+			gA += (AL == KMAJOR) ? 64 : 64 * (long long)p.lda;
+			gB += (BL == KMAJOR) ? 64 : 64 * (long long)p.ldb;
+		}
+	}
 
 	double acc[MI][NI][4];
 #pragma unroll
@@ -196,7 +231,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) k_gemm(GemmArgs p)
 #pragma unroll
 			for (int r = 0; r < 4; r++) acc[i][j][r] = 0.0;
 
-	gemm_mainloop<Cfg, AL, BL>(gA, gB, p.lda, p.ldb, task.klen, smem, acc);
+	gemm_mainloop<Cfg, AL, BL>(gA, gB, p.lda, p.ldb, klen, smem, acc);
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
