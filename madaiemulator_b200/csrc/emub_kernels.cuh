@@ -52,55 +52,14 @@ __global__ void k_theta_prep(const double *__restrict__ thetas, int B, int nth_i
 	c[3] = 0.0;
 }
 
-// ---- covariance pair functions (literal operation order of the reference) -------------------------
-template <int KERNEL>
-__device__ __forceinline__ double cov_pair(const double *xi, int si, const double *xj, int sj, int d,
-                                           const double *__restrict__ c, const double *__restrict__ tab)
-{
-	if (KERNEL == 1) {
-		// emulator.c:101-152
-		// exponent += (-1/2) dist^2 / l_k^2 (scaling by 1/2 is exact, so this is the literal sum up to the
-		// reciprocal of deviation D-5); "all |dist| < 1e-10" is tracked as one predicate
-		double e = 0.0;
-		bool same = true;
-		for (int k = 0; k < d; k++) {
-			const double dist = fabs(xi[k * si] - xj[k * sj]);
-			e += ((-0.5 * dist) * dist) * c[4 + k];
-			same = same && (dist < 0.0000000001);
-		}
-		double v = exp_neg(e, tab) * c[0];
-		if (same) v += c[1];
-		return v;
-	} else {
-		// emulator.c:344-386 (Matern 3/2), :438-480 (Matern 5/2)
-		double r2 = 0.0;
-		int cnt = 0;
-		for (int k = 0; k < d; k++) {
-			double dist = fabs(xi[k * si] - xj[k * sj]);
-			r2 += dist * dist;
-			cnt += (dist < 0.0000000000000001);
-		}
-		double dist = sqrt(r2);
-		double v;
-		if (KERNEL == 2) {
-			const double root3 = 1.732050808;
-			if (dist > 0.0) v = c[0] * (1 + root3 * (dist / c[2])) * exp_neg(-root3 * (dist / c[2]), tab);
-			else v = c[0];
-		} else {
-			const double root5 = 2.236067978;
-			double dr = dist / c[2];
-			if (dist > 0.0) v = c[0] * (1 + root5 * dr + (5.0 / 3.0) * dr * dr) * exp_neg(-root5 * dr, tab);
-			else v = c[0];
-		}
-		if (cnt == d) v += c[1];
-		return v;
-	}
-}
-
 // K1.  grid (ceil(ncols/64), ceil(nrows/64), B), 256 threads, dynamic smem 2*d*64 doubles.
 // Square mode (CROSS=false): rows and columns are design points; entries outside n x n are the identity
 // (padding); lower_only skips tiles strictly above the diagonal.
 // Cross mode: columns are query points (mq valid), clamp < 1e-10 -> 0 (emulator.c:588-590), padding is 0.
+// Each thread owns a 4 x 4 register tile of pairs; per parameter k it loads 4 + 4 coordinates once and
+// updates the 16 exponents (3 FP64 ops per pair and parameter), so the kernel is FP64-pipe bound, not
+// shared-memory bound.  "All |dist_k| below the threshold" (the nugget condition, emulator.c:136-150) is
+// tested on k = 0 for every pair and on k >= 1 only for the pairs that are still candidates.
 template <int KERNEL, bool CROSS>
 __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n, int d, const double *__restrict__ Q,
                                              int mq, const double *__restrict__ consts, long long const_stride,
@@ -112,11 +71,13 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 	double *sXi = sm;            // [d][64]
 	double *sXj = sm + d * CT;   // [d][64]
 	__shared__ double sc[CONST_STRIDE];
+	__shared__ double sh[MAXD];  // -0.5 / l_k^2 (scaling by 1/2 is exact: same bits as the literal (-1/2 dist) dist / l^2 up to D-5)
 	__shared__ double stab[64];
 	exp_table_load(stab);
 	const int tid = threadIdx.x;
 	const double *cg = consts + b * const_stride;
 	for (int i = tid; i < 4 + 3 * d; i += 256) sc[i] = cg[i];
+	if (KERNEL == 1) for (int i = tid; i < d; i += 256) sh[i] = -0.5 * cg[4 + i];
 	const int i0 = bi * CT, j0 = bj * CT;
 	const int ncols = CROSS ? mq : n;
 	const double *XJ = CROSS ? Q : X;
@@ -127,16 +88,75 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 	}
 	__syncthreads();
 	const int tx = tid & 15, ty = tid >> 4;
+	const double thr = (KERNEL == 1) ? 0.0000000001 : 0.0000000000000001;
+	double e[4][4];
+	unsigned same = 0;
+#pragma unroll
+	for (int r = 0; r < 4; r++)
+#pragma unroll
+		for (int c = 0; c < 4; c++) e[r][c] = 0.0;
+	{
+		double xi[4], xj[4];
+#pragma unroll
+		for (int r = 0; r < 4; r++) xi[r] = sXi[ty + 16 * r];
+#pragma unroll
+		for (int c = 0; c < 4; c++) xj[c] = sXj[tx + 16 * c];
+		const double h = (KERNEL == 1) ? sh[0] : 1.0;
+#pragma unroll
+		for (int r = 0; r < 4; r++)
+#pragma unroll
+			for (int c = 0; c < 4; c++) {
+				const double dist = fabs(xi[r] - xj[c]);
+				e[r][c] = (dist * dist) * h;
+				if (dist < thr) same |= 1u << (r * 4 + c);
+			}
+	}
+	for (int k = 1; k < d; k++) {
+		double xi[4], xj[4];
+#pragma unroll
+		for (int r = 0; r < 4; r++) xi[r] = sXi[k * CT + ty + 16 * r];
+#pragma unroll
+		for (int c = 0; c < 4; c++) xj[c] = sXj[k * CT + tx + 16 * c];
+		const double h = (KERNEL == 1) ? sh[k] : 1.0;
+#pragma unroll
+		for (int r = 0; r < 4; r++)
+#pragma unroll
+			for (int c = 0; c < 4; c++) {
+				const double dl = xi[r] - xj[c];
+				e[r][c] = fma(dl * dl, h, e[r][c]);
+			}
+		if (same) {  // rare: only pairs that coincide in every parameter seen so far
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+#pragma unroll
+				for (int c = 0; c < 4; c++)
+					if (!(fabs(xi[r] - xj[c]) < thr)) same &= ~(1u << (r * 4 + c));
+		}
+	}
 	double *o = out + b * out_stride;
 #pragma unroll
 	for (int r = 0; r < 4; r++) {
-		const int li = ty + 16 * r, gi = i0 + li;
+		const int gi = i0 + ty + 16 * r;
 #pragma unroll
 		for (int c = 0; c < 4; c++) {
-			const int lj = tx + 16 * c, gj = j0 + lj;
+			const int gj = j0 + tx + 16 * c;
 			double v;
 			if (gi < n && gj < ncols) {
-				v = cov_pair<KERNEL>(sXi + li, CT, sXj + lj, CT, d, sc, stab);
+				if (KERNEL == 1) {
+					v = exp_neg(e[r][c], stab) * sc[0];  // emulator.c:134
+				} else {
+					// emulator.c:344-386 (Matern 3/2), :438-480 (Matern 5/2); e holds the squared distance
+					const double dist = sqrt(e[r][c]);
+					if (KERNEL == 2) {
+						const double root3 = 1.732050808;
+						v = (dist > 0.0) ? sc[0] * (1 + root3 * (dist / sc[2])) * exp_neg(-root3 * (dist / sc[2]), stab) : sc[0];
+					} else {
+						const double root5 = 2.236067978;
+						const double dr = dist / sc[2];
+						v = (dist > 0.0) ? sc[0] * (1 + root5 * dr + (5.0 / 3.0) * dr * dr) * exp_neg(-root5 * dr, stab) : sc[0];
+					}
+				}
+				if (same & (1u << (r * 4 + c))) v += sc[1];
 				if (CROSS && v < 1E-10) v = 0.0;
 			} else {
 				v = (!CROSS && gi == gj) ? 1.0 : 0.0;
