@@ -58,6 +58,10 @@ int emub_model_slots(const emub_model *m);
 /* replace the training vector (same design): the PCA components of one multivariate model share X
  * (multi_modelstruct.c:121-148) */
 int emub_model_set_training(emub_model *m, const double *y);
+/* several training vectors on one design: Y is n x ncomp row-major (row stride ldy), e.g. the pca_zmatrix of a
+ * multivariate model (multi_modelstruct.c:295-316); component c is column c */
+int emub_model_set_training_multi(emub_model *m, const double *Y, int ldy, int ncomp);
+int emub_model_ncomponents(const emub_model *m);
 
 /* makeCovMatrix_fnptr (emulator.c:636): C (n x n, row stride ldc) at the FULL theta vector */
 int emub_cov_matrix(emub_model *m, const double *thetas, double *C, int ldc);
@@ -77,6 +81,10 @@ int emub_k_vectors(emub_model *m, const double *thetas, const double *pts, int l
  */
 int emub_loglik_grad_batch(emub_model *m, const double *thetas, int B, int want_grad,
                            double *negL, double *grad, double *sigma2, int *status);
+/* same with a training-vector (PCA component) index per point: comp[B] (NULL = component 0).  This is how the restart
+ * fronts of all components of a multivariate model (estimate_multi, multivar_support.c:20-27) share one batch */
+int emub_loglik_grad_batch_comp(emub_model *m, const double *thetas, const int *comp, int B, int want_grad,
+                                double *negL, double *grad, double *sigma2, int *status);
 /* same, but thetas / outputs are DEVICE pointers (out: B x (nthetas+2) doubles per point:
  * negL, sigma2, status, logdet, grad[nthetas-1]); asynchronous on the context's streams until
  * emub_ctx_synchronize. */
@@ -89,10 +97,17 @@ int emub_loglik_extras(emub_model *m, int b, double *logdet, double *beta);
 /* alloc_emulator_struct (emulator_struct.c:13): covariance at the FULL thetas, Cholesky, the
  * cached C^-1-derived quantities and beta.  Returns EMUB_EDOM / EMUB_EREG where the reference exits. */
 int emub_emulator_create(emub_model *m, const double *thetas, emub_emulator **out);
+int emub_emulator_create_comp(emub_model *m, int comp, const double *thetas, emub_emulator **out);
 void emub_emulator_destroy(emub_emulator *e);
 int emub_emulator_beta(emub_emulator *e, double *beta); /* p values */
 /* emulate_point (emulator_struct.c:124) for mq points: pts (mq x d, row stride ldp) -> mean[mq], var[mq] */
 int emub_predict_batch(emub_emulator *e, const double *pts, int ldp, int mq, double *mean, double *var);
+/* emulate_point_multi (multivar_support.c:103-157) for mq points: all nr PCA components (emulators of one model) and
+ * the back-projection  mean_i = ybar_i + sum_j U_ij sqrt(lambda_j) m_j,  var_i = sum_j U_ij^2 lambda_j v_j  on the
+ * device; evecs is nt x nr row-major.  mean, var: mq x nt.  nt = 0: PCA-space output mq x nr
+ * (emulate_point_multi_pca, multivar_support.c:78) */
+int emub_predict_multi(emub_emulator *const *emus, int nr, const double *pts, int ldp, int mq, int nt,
+                       const double *training_mean, const double *evecs, const double *evals, double *mean, double *var);
 /* device-pointer variant: d_pts is mq x d contiguous; asynchronous */
 int emub_predict_batch_dev(emub_emulator *e, const double *d_pts, int mq, double *d_mean, double *d_var);
 

@@ -88,7 +88,10 @@ struct emub_model {
 	emub_ctx *ctx;
 	int n, d, p, ncp, kernel, order, nth, npad, nblk, nslots;
 	size_t mat;  // npad * npad
-	double *dX, *dy, *dYh;
+	double *dX, *dy, *dYh;  // dYh: ncomp x npad x ncp
+	int ncomp;              // training vectors sharing the design (PCA components, multi_modelstruct.c:121-148)
+	int *dComp, *hComp;     // component evaluated by each slot of the current chunk
+	struct QueryWs *qws;    // query workspace shared by every emulator of this model (lazily allocated)
 	GemmTask *dTasks;
 	std::vector<FactorStep> steps;
 	int lauum_off, lauum_cnt;
@@ -100,14 +103,21 @@ struct emub_model {
 	int last_count;
 };
 
+// query workspace: one chunk of up to mqc points
+struct QueryWs {
+	int mqc;      // query chunk (multiple of 128)
+	int ncomp;    // rows of dMean / dVar
+	double *dQ, *dK, *dVsq, *dKA, *dMean, *dVar;  // dMean, dVar: ncomp x mqc
+	double *dOutM, *dOutV, *dProj;                // back-projected outputs (mqc x ntmax), projection data
+	GemmTask *dTasks;
+	double *hQ, *hOut;  // pinned
+};
+constexpr int NTMAX = 64;  // observables per multivariate model supported by the fused back-projection
+
 struct emub_emulator {
 	emub_model *m;
 	double *W, *AB, *beta, *Minv, *consts;
 	double kappa;
-	int mqc;  // query chunk (multiple of 128)
-	double *dQ, *dK, *dVsq, *dKA, *dMean, *dVar;
-	GemmTask *dTasks;
-	double *hQ, *hOut;  // pinned
 	double hbeta[MAXNCP];
 };
 
@@ -248,6 +258,7 @@ static void build_schedules(emub_model *m, std::vector<GemmTask> &tasks)
 	m->lauum_cnt = (int)tasks.size() - m->lauum_off;
 }
 
+static void free_query_ws(emub_model *m);
 static int regression_fns(int order, int d) { if (order < 0 || order > 3) order = 0; return 1 + order * d; }
 
 extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n, int d, const double *y, int kernel,
@@ -283,6 +294,8 @@ extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n,
 	CUDA_TRY(cudaMalloc(&m->dy, sizeof(double) * n));
 	CUDA_TRY(cudaMemcpy(m->dy, y, sizeof(double) * n, cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaMalloc(&m->dYh, sizeof(double) * (size_t)m->npad * m->ncp));
+	m->ncomp = 1;
+	m->qws = nullptr;
 	std::vector<GemmTask> tasks;
 	build_schedules(m, tasks);
 	if (tasks.empty()) tasks.push_back({0, 0, 0, 0, 0});
@@ -306,12 +319,15 @@ extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n,
 	CUDA_TRY(cudaMalloc(&m->dThetas, S * (MAXD + 2) * sizeof(double)));
 	CUDA_TRY(cudaMalloc(&m->dOut, S * (MAXD + 6) * sizeof(double)));
 	CUDA_TRY(cudaMalloc(&m->dInfo, S * sizeof(int)));
+	CUDA_TRY(cudaMalloc(&m->dComp, S * sizeof(int)));
+	CUDA_TRY(cudaMemset(m->dComp, 0, S * sizeof(int)));
+	CUDA_TRY(cudaMallocHost(&m->hComp, S * sizeof(int)));
 	CUDA_TRY(cudaMallocHost(&m->hThetas, S * (MAXD + 2) * sizeof(double)));
 	CUDA_TRY(cudaMallocHost(&m->hRes, S * RES_STRIDE * sizeof(double)));
 	cudaStream_t st = ctx->streams[0];
 	{
 		LaunchScope ls(ctx, EMUB_K_SMALL, 0, st);
-		k_build_yh<<<(m->npad + 127) / 128, 128, 0, st>>>(m->dX, m->dy, n, m->npad, d, order, m->ncp, m->dYh);
+		k_build_yh<<<(m->npad + 127) / 128, 128, 0, st>>>(m->dX, m->dy, 1, n, m->npad, d, order, m->ncp, m->dYh);
 	}
 	CUDA_TRY(cudaStreamSynchronize(st));
 	CUDA_TRY(cudaGetLastError());
@@ -328,25 +344,58 @@ extern "C" void emub_model_destroy(emub_model *m)
 	cudaFree(m->bufA); cudaFree(m->bufW); cudaFree(m->bufT);
 	cudaFree(m->dUG); cudaFree(m->dAB); cudaFree(m->dConsts); cudaFree(m->dLogdet); cudaFree(m->dGramPart);
 	cudaFree(m->dRes); cudaFree(m->dGradPart); cudaFree(m->dMinv); cudaFree(m->dThetas); cudaFree(m->dOut); cudaFree(m->dInfo);
-	cudaFreeHost(m->hThetas); cudaFreeHost(m->hRes);
+	cudaFree(m->dComp);
+	cudaFreeHost(m->hThetas); cudaFreeHost(m->hRes); cudaFreeHost(m->hComp);
+	free_query_ws(m);
 	delete m;
 }
 extern "C" int emub_model_nthetas(const emub_model *m) { return m ? m->nth : 0; }
 extern "C" int emub_model_nregression_fns(const emub_model *m) { return m ? m->p : 0; }
 extern "C" int emub_model_slots(const emub_model *m) { return m ? m->nslots : 0; }
 
+static void free_query_ws(emub_model *m)
+{
+	QueryWs *w = m->qws;
+	if (!w) return;
+	cudaFree(w->dQ); cudaFree(w->dK); cudaFree(w->dVsq); cudaFree(w->dKA); cudaFree(w->dMean); cudaFree(w->dVar);
+	cudaFree(w->dOutM); cudaFree(w->dOutV); cudaFree(w->dProj); cudaFree(w->dTasks);
+	cudaFreeHost(w->hQ); cudaFreeHost(w->hOut);
+	delete w;
+	m->qws = nullptr;
+}
+
+extern "C" int emub_model_set_training_multi(emub_model *m, const double *Y, int ldy, int ncomp)
+{
+	if (!m || !Y || ncomp < 1 || ldy < ncomp) return set_err(EMUB_EINVAL, "emub_model_set_training_multi: bad argument%s");
+	CUDA_TRY(cudaSetDevice(m->ctx->device));
+	CUDA_TRY(cudaDeviceSynchronize());
+	cudaStream_t st = m->ctx->streams[0];
+	double *dY = nullptr;
+	CUDA_TRY(cudaMalloc(&dY, sizeof(double) * (size_t)m->n * ncomp));
+	CUDA_TRY(cudaMemcpy2D(dY, sizeof(double) * ncomp, Y, sizeof(double) * ldy, sizeof(double) * ncomp, m->n, cudaMemcpyHostToDevice));
+	if (ncomp != m->ncomp) {
+		cudaFree(m->dYh);
+		CUDA_TRY(cudaMalloc(&m->dYh, sizeof(double) * (size_t)ncomp * m->npad * m->ncp));
+		m->ncomp = ncomp;
+		free_query_ws(m);
+	}
+	for (int c = 0; c < ncomp; c++) {
+		LaunchScope ls(m->ctx, EMUB_K_SMALL, 0, st);
+		k_build_yh<<<(m->npad + 127) / 128, 128, 0, st>>>(m->dX, dY + c, ncomp, m->n, m->npad, m->d, m->order, m->ncp,
+		                                                   m->dYh + (size_t)c * m->npad * m->ncp);
+	}
+	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(cudaGetLastError());
+	cudaFree(dY);
+	return EMUB_OK;
+}
+
+extern "C" int emub_model_ncomponents(const emub_model *m) { return m ? m->ncomp : 0; }
+
 extern "C" int emub_model_set_training(emub_model *m, const double *y)
 {
 	if (!m || !y) return set_err(EMUB_EINVAL, "emub_model_set_training: null%s");
-	CUDA_TRY(cudaSetDevice(m->ctx->device));
-	cudaStream_t st = m->ctx->streams[0];
-	CUDA_TRY(cudaMemcpyAsync(m->dy, y, sizeof(double) * m->n, cudaMemcpyHostToDevice, st));
-	{
-		LaunchScope ls(m->ctx, EMUB_K_SMALL, 0, st);
-		k_set_y<<<(m->n + 127) / 128, 128, 0, st>>>(m->dy, m->n, m->ncp, m->dYh);
-	}
-	CUDA_TRY(cudaStreamSynchronize(st));
-	return EMUB_OK;
+	return emub_model_set_training_multi(m, y, 1, 1);
 }
 
 // ---- kernel launch helpers ----------------------------------------------------------------------------
@@ -439,7 +488,7 @@ static void run_regression(emub_model *m, cudaStream_t st, int s0, int count, in
 	double *UG = m->dUG + (size_t)s0 * sUG;
 	{
 		LaunchScope ls(c, EMUB_K_SKINNY, count * 4.0 * (double)m->mat * nchunk_cols, st);
-		k_tri_rows_times<<<dim3(m->npad / 32, nchunk_cols, count), 256, 0, st>>>(W, (long long)m->mat, m->npad, m->dYh, 0, m->ncp, UG, sUG);
+		k_tri_rows_times<<<dim3(m->npad / 32, nchunk_cols, count), 256, 0, st>>>(W, (long long)m->mat, m->npad, m->dYh, sUG, m->dComp + s0, m->ncp, UG, sUG);
 	}
 	{
 		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
@@ -535,6 +584,18 @@ static int run_chunk(emub_model *m, int count, int nth_in, int mode, int want_gr
 	return EMUB_OK;
 }
 
+// component of every slot of the chunk -> dComp (NULL: component 0)
+static int upload_components(emub_model *m, const int *comp, int done, int count, cudaStream_t st)
+{
+	for (int b = 0; b < count; b++) {
+		const int cidx = comp ? comp[done + b] : 0;
+		if (cidx < 0 || cidx >= m->ncomp) return set_err(EMUB_EINVAL, "emub: component index out of range%s");
+		m->hComp[b] = cidx;
+	}
+	CUDA_TRY(cudaMemcpyAsync(m->dComp, m->hComp, sizeof(int) * count, cudaMemcpyHostToDevice, st));
+	return EMUB_OK;
+}
+
 extern "C" int emub_loglik_grad_batch_dev(emub_model *m, const double *d_thetas, int B, int want_grad, double *d_out)
 {
 	if (!m || !d_thetas || !d_out || B < 0) return set_err(EMUB_EINVAL, "emub_loglik_grad_batch_dev: bad argument%s");
@@ -544,8 +605,10 @@ extern "C" int emub_loglik_grad_batch_dev(emub_model *m, const double *d_thetas,
 	cudaStream_t st = c->streams[0];
 	for (int done = 0; done < B; done += m->nslots) {
 		const int count = std::min(m->nslots, B - done);
+		int rc = upload_components(m, nullptr, done, count, st);
+		if (rc) return rc;
 		CUDA_TRY(cudaMemcpyAsync(m->dThetas, d_thetas + (size_t)done * nth1, sizeof(double) * count * nth1, cudaMemcpyDeviceToDevice, st));
-		int rc = run_chunk(m, count, nth1, THETA_LIK, want_grad, 0);
+		rc = run_chunk(m, count, nth1, THETA_LIK, want_grad, 0);
 		if (rc) return rc;
 		{
 			LaunchScope ls(c, EMUB_K_SMALL, 0, st);
@@ -556,8 +619,8 @@ extern "C" int emub_loglik_grad_batch_dev(emub_model *m, const double *d_thetas,
 	return EMUB_OK;
 }
 
-extern "C" int emub_loglik_grad_batch(emub_model *m, const double *thetas, int B, int want_grad, double *negL, double *grad,
-                                      double *sigma2, int *status)
+extern "C" int emub_loglik_grad_batch_comp(emub_model *m, const double *thetas, const int *comp, int B, int want_grad,
+                                           double *negL, double *grad, double *sigma2, int *status)
 {
 	if (!m || !thetas || B < 0) return set_err(EMUB_EINVAL, "emub_loglik_grad_batch: bad argument%s");
 	emub_ctx *c = m->ctx;
@@ -566,9 +629,11 @@ extern "C" int emub_loglik_grad_batch(emub_model *m, const double *thetas, int B
 	cudaStream_t st = c->streams[0];
 	for (int done = 0; done < B; done += m->nslots) {
 		const int count = std::min(m->nslots, B - done);
+		int rc = upload_components(m, comp, done, count, st);
+		if (rc) return rc;
 		memcpy(m->hThetas, thetas + (size_t)done * nth1, sizeof(double) * count * nth1);
 		CUDA_TRY(cudaMemcpyAsync(m->dThetas, m->hThetas, sizeof(double) * count * nth1, cudaMemcpyHostToDevice, st));
-		int rc = run_chunk(m, count, nth1, THETA_LIK, want_grad, 0);
+		rc = run_chunk(m, count, nth1, THETA_LIK, want_grad, 0);
 		if (rc) return rc;
 		CUDA_TRY(cudaMemcpyAsync(m->hRes, m->dRes, sizeof(double) * count * RES_STRIDE, cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
@@ -583,6 +648,12 @@ extern "C" int emub_loglik_grad_batch(emub_model *m, const double *thetas, int B
 		}
 	}
 	return EMUB_OK;
+}
+
+extern "C" int emub_loglik_grad_batch(emub_model *m, const double *thetas, int B, int want_grad, double *negL, double *grad,
+                                      double *sigma2, int *status)
+{
+	return emub_loglik_grad_batch_comp(m, thetas, nullptr, B, want_grad, negL, grad, sigma2, status);
 }
 
 extern "C" int emub_loglik_extras(emub_model *m, int b, double *logdet, double *beta)
@@ -705,17 +776,50 @@ extern "C" int emub_debug_cholesky(emub_model *m, const double *theta_less_amp, 
 }
 
 // ---- prediction ------------------------------------------------------------------------------------------
-extern "C" int emub_emulator_create(emub_model *m, const double *thetas, emub_emulator **out)
+static int ensure_query_ws(emub_model *m)
+{
+	if (m->qws) return EMUB_OK;
+	QueryWs *w = new QueryWs();
+	memset(w, 0, sizeof(*w));
+	m->qws = w;
+	// chunk of up to 16384 points, K (npad x mqc) bounded to ~1 GiB
+	int mqc = 16384;
+	while (mqc > TB && (size_t)m->npad * mqc * sizeof(double) > ((size_t)1 << 30)) mqc /= 2;
+	w->mqc = mqc;
+	w->ncomp = m->ncomp;
+	CUDA_TRY(cudaMalloc(&w->dQ, sizeof(double) * (size_t)mqc * m->d));
+	CUDA_TRY(cudaMalloc(&w->dK, sizeof(double) * (size_t)m->npad * mqc));
+	CUDA_TRY(cudaMalloc(&w->dVsq, sizeof(double) * (size_t)m->nblk * DefaultCfg::SUBM * mqc));
+	CUDA_TRY(cudaMalloc(&w->dKA, sizeof(double) * (size_t)mqc * m->ncp));
+	CUDA_TRY(cudaMalloc(&w->dMean, sizeof(double) * (size_t)w->ncomp * mqc));
+	CUDA_TRY(cudaMalloc(&w->dVar, sizeof(double) * (size_t)w->ncomp * mqc));
+	CUDA_TRY(cudaMalloc(&w->dOutM, sizeof(double) * (size_t)NTMAX * mqc));
+	CUDA_TRY(cudaMalloc(&w->dOutV, sizeof(double) * (size_t)NTMAX * mqc));
+	CUDA_TRY(cudaMalloc(&w->dProj, sizeof(double) * (size_t)(NTMAX + NTMAX * NTMAX + NTMAX)));
+	CUDA_TRY(cudaMallocHost(&w->hQ, sizeof(double) * (size_t)mqc * m->d));
+	CUDA_TRY(cudaMallocHost(&w->hOut, sizeof(double) * 2 * (size_t)std::max(NTMAX, 1) * mqc));
+	// V = W K, one task per row block (longest K first); the batch dimension walks the query blocks
+	std::vector<GemmTask> tasks;
+	for (int i = m->nblk - 1; i >= 0; i--) tasks.push_back({(long long)i * TB * m->npad, 0, 0, (i + 1) * TB, i | TASK_TRIM_END_SR0});
+	CUDA_TRY(cudaMalloc(&w->dTasks, tasks.size() * sizeof(GemmTask)));
+	CUDA_TRY(cudaMemcpy(w->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
+	return EMUB_OK;
+}
+
+extern "C" int emub_emulator_create_comp(emub_model *m, int comp, const double *thetas, emub_emulator **out)
 {
 	if (!m || !thetas || !out) return set_err(EMUB_EINVAL, "emub_emulator_create: null%s");
+	if (comp < 0 || comp >= m->ncomp) return set_err(EMUB_EINVAL, "emub_emulator_create: component index out of range%s");
 	emub_ctx *c = m->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
 	cudaStream_t st = c->streams[0];
+	int rc = upload_components(m, &comp, 0, 1, st);
+	if (rc) return rc;
 	CUDA_TRY(cudaMemcpyAsync(m->dThetas, thetas, sizeof(double) * m->nth, cudaMemcpyHostToDevice, st));
 	// factorise in slot 0 on stream 0 only
 	const int saved_groups = c->ngroups;
 	c->ngroups = 1;
-	int rc = run_chunk(m, 1, m->nth, THETA_FULL, 0, 1);
+	rc = run_chunk(m, 1, m->nth, THETA_FULL, 0, 1);
 	c->ngroups = saved_groups;
 	if (rc) return rc;
 	run_wt_times(m, st, 0, 1, (m->p + 1 + 7) / 8);
@@ -727,6 +831,8 @@ extern "C" int emub_emulator_create(emub_model *m, const double *thetas, emub_em
 	const int status = (int)m->hRes[2];
 	if (status == 1) return set_err(EMUB_EDOM, "emub_emulator_create: covariance matrix not positive definite%s");
 	if (status == 2) return set_err(EMUB_EREG, "emub_emulator_create: regression matrix not positive definite%s");
+	rc = ensure_query_ws(m);
+	if (rc) return rc;
 	emub_emulator *e = new emub_emulator();
 	memset(e, 0, sizeof(*e));
 	e->m = m;
@@ -743,26 +849,14 @@ extern "C" int emub_emulator_create(emub_model *m, const double *thetas, emub_em
 	CUDA_TRY(cudaMemcpyAsync(e->beta, m->dRes + RES_BETA, MAXNCP * sizeof(double), cudaMemcpyDeviceToDevice, st));
 	CUDA_TRY(cudaMemcpyAsync(e->Minv, m->dMinv, MAXNCP * MAXNCP * sizeof(double), cudaMemcpyDeviceToDevice, st));
 	CUDA_TRY(cudaMemcpyAsync(e->consts, m->dConsts, CONST_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, st));
-	// query workspace: chunk of up to 16384 points, K (npad x mqc) bounded to ~1 GiB
-	int mqc = 16384;
-	while (mqc > TB && (size_t)m->npad * mqc * sizeof(double) > ((size_t)1 << 30)) mqc /= 2;
-	e->mqc = mqc;
-	CUDA_TRY(cudaMalloc(&e->dQ, sizeof(double) * (size_t)mqc * m->d));
-	CUDA_TRY(cudaMalloc(&e->dK, sizeof(double) * (size_t)m->npad * mqc));
-	CUDA_TRY(cudaMalloc(&e->dVsq, sizeof(double) * (size_t)m->nblk * DefaultCfg::SUBM * mqc));
-	CUDA_TRY(cudaMalloc(&e->dKA, sizeof(double) * (size_t)mqc * m->ncp));
-	CUDA_TRY(cudaMalloc(&e->dMean, sizeof(double) * mqc));
-	CUDA_TRY(cudaMalloc(&e->dVar, sizeof(double) * mqc));
-	CUDA_TRY(cudaMallocHost(&e->hQ, sizeof(double) * (size_t)mqc * m->d));
-	CUDA_TRY(cudaMallocHost(&e->hOut, sizeof(double) * 2 * mqc));
-	// V = W K, one task per row block (longest K first); the batch dimension walks the query blocks
-	std::vector<GemmTask> tasks;
-	for (int i = m->nblk - 1; i >= 0; i--) tasks.push_back({(long long)i * TB * m->npad, 0, 0, (i + 1) * TB, i | TASK_TRIM_END_SR0});
-	CUDA_TRY(cudaMalloc(&e->dTasks, tasks.size() * sizeof(GemmTask)));
-	CUDA_TRY(cudaMemcpyAsync(e->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
 	*out = e;
 	return EMUB_OK;
+}
+
+extern "C" int emub_emulator_create(emub_model *m, const double *thetas, emub_emulator **out)
+{
+	return emub_emulator_create_comp(m, 0, thetas, out);
 }
 
 extern "C" void emub_emulator_destroy(emub_emulator *e)
@@ -771,8 +865,6 @@ extern "C" void emub_emulator_destroy(emub_emulator *e)
 	cudaSetDevice(e->m->ctx->device);
 	cudaDeviceSynchronize();
 	cudaFree(e->W); cudaFree(e->AB); cudaFree(e->beta); cudaFree(e->Minv); cudaFree(e->consts);
-	cudaFree(e->dQ); cudaFree(e->dK); cudaFree(e->dVsq); cudaFree(e->dKA); cudaFree(e->dMean); cudaFree(e->dVar); cudaFree(e->dTasks);
-	cudaFreeHost(e->hQ); cudaFreeHost(e->hOut);
 	delete e;
 }
 
@@ -788,21 +880,22 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 {
 	emub_model *m = e->m;
 	emub_ctx *c = m->ctx;
+	QueryWs *w = m->qws;
 	const int mq_pad = (mq + TB - 1) / TB * TB;
-	const int ldk = e->mqc;
-	launch_kcross(m, st, e->consts, dQ, mq, mq_pad, e->dK, ldk);
+	const int ldk = w->mqc;
+	launch_kcross(m, st, e->consts, dQ, mq, mq_pad, w->dK, ldk);
 	const int nqb = mq_pad / TB;
 	// |W k|^2 partials: tile (row block i, query block qb)
-	launch_gemm<KMAJOR, RMAJOR, EPI_COLSUMSQ>(c, EMUB_K_GEMM_PRED, (double)m->npad * (m->npad + TB / 2) * TB, st, e->dTasks, m->nblk, nqb,
-	                                          e->W, 0, m->npad, e->dK, TB, ldk, e->dVsq, TB, ldk, 1.0);
+	launch_gemm<KMAJOR, RMAJOR, EPI_COLSUMSQ>(c, EMUB_K_GEMM_PRED, (double)m->npad * (m->npad + TB / 2) * TB, st, w->dTasks, m->nblk, nqb,
+	                                          e->W, 0, m->npad, w->dK, TB, ldk, w->dVsq, TB, ldk, 1.0);
 	{
 		const int nchunk_cols = (m->p + 1 + 7) / 8;
 		LaunchScope ls(c, EMUB_K_SKINNY, 8.0 * (double)m->npad * mq_pad * nchunk_cols, st);
-		k_cols_times<false><<<dim3(mq_pad / 32, nchunk_cols, 1), 256, 0, st>>>(e->dK, 0, ldk, m->npad, e->AB, 0, m->ncp, e->dKA, 0);
+		k_cols_times<false><<<dim3(mq_pad / 32, nchunk_cols, 1), 256, 0, st>>>(w->dK, 0, ldk, m->npad, e->AB, 0, m->ncp, w->dKA, 0);
 	}
 	{
 		LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);
-		k_pred_final<<<(mq + 127) / 128, 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, e->dKA, m->ncp, e->dVsq, m->nblk * DefaultCfg::SUBM, ldk, e->beta,
+		k_pred_final<<<(mq + 127) / 128, 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, m->nblk * DefaultCfg::SUBM, ldk, e->beta,
 		                                               e->Minv, e->kappa, dMean, dVar);
 	}
 	CUDA_TRY(cudaGetLastError());
@@ -814,9 +907,11 @@ extern "C" int emub_predict_batch_dev(emub_emulator *e, const double *d_pts, int
 	if (!e || !d_pts || !d_mean || !d_var || mq < 0) return set_err(EMUB_EINVAL, "emub_predict_batch_dev: bad argument%s");
 	emub_model *m = e->m;
 	CUDA_TRY(cudaSetDevice(m->ctx->device));
+	{ int rc0 = ensure_query_ws(m); if (rc0) return rc0; }
 	cudaStream_t st = m->ctx->streams[0];
-	for (int done = 0; done < mq; done += e->mqc) {
-		const int cnt = std::min(e->mqc, mq - done);
+	const int mqc = m->qws->mqc;
+	for (int done = 0; done < mq; done += mqc) {
+		const int cnt = std::min(mqc, mq - done);
 		int rc = predict_chunk(e, st, d_pts + (size_t)done * m->d, cnt, d_mean + done, d_var + done);
 		if (rc) return rc;
 	}
@@ -828,18 +923,83 @@ extern "C" int emub_predict_batch(emub_emulator *e, const double *pts, int ldp, 
 	if (!e || !pts || !mean || !var || mq < 0 || ldp < e->m->d) return set_err(EMUB_EINVAL, "emub_predict_batch: bad argument%s");
 	emub_model *m = e->m;
 	CUDA_TRY(cudaSetDevice(m->ctx->device));
+	{ int rc0 = ensure_query_ws(m); if (rc0) return rc0; }
+	QueryWs *w = m->qws;
 	cudaStream_t st = m->ctx->streams[0];
-	for (int done = 0; done < mq; done += e->mqc) {
-		const int cnt = std::min(e->mqc, mq - done);
-		for (int q = 0; q < cnt; q++) memcpy(e->hQ + (size_t)q * m->d, pts + (size_t)(done + q) * ldp, sizeof(double) * m->d);
-		CUDA_TRY(cudaMemcpyAsync(e->dQ, e->hQ, sizeof(double) * (size_t)cnt * m->d, cudaMemcpyHostToDevice, st));
-		int rc = predict_chunk(e, st, e->dQ, cnt, e->dMean, e->dVar);
+	for (int done = 0; done < mq; done += w->mqc) {
+		const int cnt = std::min(w->mqc, mq - done);
+		for (int q = 0; q < cnt; q++) memcpy(w->hQ + (size_t)q * m->d, pts + (size_t)(done + q) * ldp, sizeof(double) * m->d);
+		CUDA_TRY(cudaMemcpyAsync(w->dQ, w->hQ, sizeof(double) * (size_t)cnt * m->d, cudaMemcpyHostToDevice, st));
+		int rc = predict_chunk(e, st, w->dQ, cnt, w->dMean, w->dVar);
 		if (rc) return rc;
-		CUDA_TRY(cudaMemcpyAsync(e->hOut, e->dMean, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
-		CUDA_TRY(cudaMemcpyAsync(e->hOut + e->mqc, e->dVar, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaMemcpyAsync(w->hOut, w->dMean, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaMemcpyAsync(w->hOut + w->mqc, w->dVar, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
-		memcpy(mean + done, e->hOut, sizeof(double) * cnt);
-		memcpy(var + done, e->hOut + e->mqc, sizeof(double) * cnt);
+		memcpy(mean + done, w->hOut, sizeof(double) * cnt);
+		memcpy(var + done, w->hOut + w->mqc, sizeof(double) * cnt);
 	}
+	return EMUB_OK;
+}
+
+// emulate_point_multi (multivar_support.c:103-157) for mq points: every PCA component's (mean, var) for the whole
+// chunk, then the back-projection to the nt observables on the device.  emus: nr emulators of ONE model.
+// mean / var: mq x nt row-major.  With nt = 0 the PCA-space values are returned instead (emulate_point_multi_pca,
+// multivar_support.c:78): mean / var are then mq x nr.
+extern "C" int emub_predict_multi(emub_emulator *const *emus, int nr, const double *pts, int ldp, int mq, int nt,
+                                  const double *training_mean, const double *evecs, const double *evals, double *mean,
+                                  double *var)
+{
+	if (!emus || nr < 1 || !pts || !mean || !var || mq < 0) return set_err(EMUB_EINVAL, "emub_predict_multi: bad argument%s");
+	emub_model *m = emus[0]->m;
+	for (int j = 0; j < nr; j++)
+		if (!emus[j] || emus[j]->m != m) return set_err(EMUB_EINVAL, "emub_predict_multi: emulators must share one model%s");
+	if (nt > NTMAX || nr > NTMAX || (nt > 0 && (!training_mean || !evecs || !evals)) || ldp < m->d)
+		return set_err(EMUB_EINVAL, "emub_predict_multi: bad projection arguments%s");
+	CUDA_TRY(cudaSetDevice(m->ctx->device));
+	{ int rc0 = ensure_query_ws(m); if (rc0) return rc0; }
+	QueryWs *w = m->qws;
+	if (nr > w->ncomp) return set_err(EMUB_EINVAL, "emub_predict_multi: more emulators than model components%s");
+	cudaStream_t st = m->ctx->streams[0];
+	if (nt > 0) {
+		// projection data: ybar[nt] | evecs[nt x nr] | evals[nr]
+		std::vector<double> proj((size_t)nt + (size_t)nt * nr + nr);
+		memcpy(proj.data(), training_mean, sizeof(double) * nt);
+		memcpy(proj.data() + nt, evecs, sizeof(double) * (size_t)nt * nr);
+		memcpy(proj.data() + nt + (size_t)nt * nr, evals, sizeof(double) * nr);
+		CUDA_TRY(cudaMemcpy(w->dProj, proj.data(), sizeof(double) * proj.size(), cudaMemcpyHostToDevice));
+	}
+	const int nout = nt > 0 ? nt : nr;
+	for (int done = 0; done < mq; done += w->mqc) {
+		const int cnt = std::min(w->mqc, mq - done);
+		for (int q = 0; q < cnt; q++) memcpy(w->hQ + (size_t)q * m->d, pts + (size_t)(done + q) * ldp, sizeof(double) * m->d);
+		CUDA_TRY(cudaMemcpyAsync(w->dQ, w->hQ, sizeof(double) * (size_t)cnt * m->d, cudaMemcpyHostToDevice, st));
+		for (int j = 0; j < nr; j++) {
+			int rc = predict_chunk(emus[j], st, w->dQ, cnt, w->dMean + (size_t)j * w->mqc, w->dVar + (size_t)j * w->mqc);
+			if (rc) return rc;
+		}
+		if (nt > 0) {
+			{
+				LaunchScope ls(m->ctx, EMUB_K_PRED_FINAL, 0, st);
+				k_backproject<<<(cnt + 127) / 128, 128, 0, st>>>(w->dMean, w->dVar, w->mqc, cnt, nt, nr, w->dProj, w->dProj + nt,
+				                                                 w->dProj + nt + (size_t)nt * nr, w->dOutM, w->dOutV);
+			}
+			CUDA_TRY(cudaMemcpyAsync(w->hOut, w->dOutM, sizeof(double) * (size_t)cnt * nt, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpyAsync(w->hOut + (size_t)NTMAX * w->mqc, w->dOutV, sizeof(double) * (size_t)cnt * nt, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaStreamSynchronize(st));
+			memcpy(mean + (size_t)done * nt, w->hOut, sizeof(double) * (size_t)cnt * nt);
+			memcpy(var + (size_t)done * nt, w->hOut + (size_t)NTMAX * w->mqc, sizeof(double) * (size_t)cnt * nt);
+		} else {
+			CUDA_TRY(cudaMemcpy2DAsync(w->hOut, sizeof(double) * cnt, w->dMean, sizeof(double) * w->mqc, sizeof(double) * cnt, nr, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpy2DAsync(w->hOut + (size_t)NTMAX * w->mqc, sizeof(double) * cnt, w->dVar, sizeof(double) * w->mqc, sizeof(double) * cnt, nr, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaStreamSynchronize(st));
+			for (int q = 0; q < cnt; q++)
+				for (int j = 0; j < nr; j++) {
+					mean[(size_t)(done + q) * nr + j] = w->hOut[(size_t)j * cnt + q];
+					var[(size_t)(done + q) * nr + j] = w->hOut[(size_t)NTMAX * w->mqc + (size_t)j * cnt + q];
+				}
+		}
+		(void)nout;
+	}
+	CUDA_TRY(cudaGetLastError());
 	return EMUB_OK;
 }

@@ -167,15 +167,16 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 }
 
 // Yh = [ y | H | 0 ] (npad x ncp), H per regression.c:9-67; rows >= n are zero.
-__global__ void k_build_yh(const double *__restrict__ X, const double *__restrict__ y, int n, int npad, int d, int order,
-                           int ncp, double *__restrict__ Yh)
+// y is read with stride ystride (component c of an n x ncomp training matrix: y + c, stride ncomp)
+__global__ void k_build_yh(const double *__restrict__ X, const double *__restrict__ y, int ystride, int n, int npad, int d,
+                           int order, int ncp, double *__restrict__ Yh)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= npad) return;
 	double *row = Yh + (size_t)i * ncp;
 	for (int c = 0; c < ncp; c++) row[c] = 0.0;
 	if (i >= n) return;
-	row[0] = y[i];
+	row[0] = y[(size_t)i * ystride];
 	row[1] = 1.0;
 	const double *x = X + (size_t)i * d;
 	if (order >= 1) for (int k = 0; k < d; k++) row[2 + k] = x[k];
@@ -344,15 +345,17 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 // ---- skinny products ---------------------------------------------------------------------------------
 // (a) OUT[i][c0..c0+8) = sum_{j <= i} W[i][j] * V[j][c0..c0+8)   (W lower triangular, npad x npad)
 // grid (npad/32, ncp/8, B), 256 threads: one warp per 4 rows.
+// V of slot b is Vbase + comp[b] * strideV (the training vector / PCA component the slot evaluates)
 __global__ void __launch_bounds__(256) k_tri_rows_times(const double *__restrict__ Wbase, long long strideW, int ld,
-                                                        const double *__restrict__ Vbase, long long strideV, int ncp,
+                                                        const double *__restrict__ Vbase, long long strideV,
+                                                        const int *__restrict__ comp, int ncp,
                                                         double *__restrict__ Obase, long long strideO)
 {
 	const int b = blockIdx.z, c0 = blockIdx.y * 8;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int r0 = blockIdx.x * 32 + warp * 4;
 	const double *W = Wbase + b * strideW;
-	const double *V = Vbase + b * strideV;
+	const double *V = Vbase + (comp ? comp[b] : 0) * strideV;
 	double acc[4][8];
 #pragma unroll
 	for (int r = 0; r < 4; r++)
@@ -787,6 +790,27 @@ __global__ void __launch_bounds__(128) k_pred_final(const double *__restrict__ Q
 	for (int k = 0; k < nblk; k++) vs += vsq_part[(size_t)k * ldq + q];
 	mean[q] = hb + ka[0];
 	var[q] = kappa - vs + reg;
+}
+
+// PCA back-projection (multivar_support.c:126-151): mean_i = ybar_i + sum_j U_ij sqrt(lambda_j) m_j,
+// var_i = sum_j U_ij^2 lambda_j v_j.  pm / pv: [nr][ldq] per-component predictions; out: [mq][nt].
+__global__ void __launch_bounds__(128) k_backproject(const double *__restrict__ pm, const double *__restrict__ pv, int ldq,
+                                                     int mq, int nt, int nr, const double *__restrict__ ybar,
+                                                     const double *__restrict__ evecs, const double *__restrict__ evals,
+                                                     double *__restrict__ mean_out, double *__restrict__ var_out)
+{
+	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= mq) return;
+	for (int i = 0; i < nt; i++) {
+		double s = 0.0, v = 0.0;
+		for (int j = 0; j < nr; j++) {
+			const double u = evecs[i * nr + j];
+			s += u * sqrt(evals[j]) * pm[(size_t)j * ldq + q];
+			v += (u * u) * evals[j] * pv[(size_t)j * ldq + q];
+		}
+		mean_out[(size_t)q * nt + i] = ybar[i] + s;
+		var_out[(size_t)q * nt + i] = v;
+	}
 }
 
 }  // namespace emub

@@ -29,7 +29,8 @@ FAMILIES = ["cov", "potf2", "gemm_chol", "gemm_trtri", "gemm_lauum", "skinny", "
 SYMBOLS = [
     "emub_ctx_create", "emub_ctx_destroy", "emub_last_error", "emub_version", "emub_ctx_stream",
     "emub_ctx_set_groups", "emub_model_create", "emub_model_destroy", "emub_model_nthetas",
-    "emub_model_nregression_fns", "emub_model_slots", "emub_model_set_training", "emub_cov_matrix",
+    "emub_model_nregression_fns", "emub_model_slots", "emub_model_set_training", "emub_model_set_training_multi",
+    "emub_model_ncomponents", "emub_loglik_grad_batch_comp", "emub_emulator_create_comp", "emub_predict_multi", "emub_cov_matrix",
     "emub_h_matrix", "emub_k_vectors", "emub_loglik_grad_batch", "emub_loglik_grad_batch_dev",
     "emub_ctx_synchronize", "emub_loglik_extras", "emub_emulator_create", "emub_emulator_destroy",
     "emub_emulator_beta", "emub_predict_batch", "emub_predict_batch_dev", "emub_profile_enable",
@@ -74,6 +75,11 @@ def lib():
     L.emub_model_nregression_fns.argtypes = [_vp]
     L.emub_model_slots.argtypes = [_vp]
     L.emub_model_set_training.argtypes = [_vp, _dp]
+    L.emub_model_set_training_multi.argtypes = [_vp, _dp, _ci, _ci]
+    L.emub_model_ncomponents.argtypes = [_vp]
+    L.emub_loglik_grad_batch_comp.argtypes = [_vp, _dp, _ip, _ci, _ci, _dp, _dp, _dp, _ip]
+    L.emub_emulator_create_comp.argtypes = [_vp, _ci, _dp, ctypes.POINTER(_vp)]
+    L.emub_predict_multi.argtypes = [ctypes.POINTER(_vp), _ci, _dp, _ci, _ci, _ci, _dp, _dp, _dp, _dp, _dp]
     L.emub_cov_matrix.argtypes = [_vp, _dp, _dp, _ci]
     L.emub_h_matrix.argtypes = [_vp, _dp, _ci]
     L.emub_k_vectors.argtypes = [_vp, _dp, _dp, _ci, _ci, _dp, _ci]
@@ -187,6 +193,13 @@ class Model:
         self.y = _c(y)
         _check(self.L.emub_model_set_training(self.h, _P(self.y)))
 
+    def set_training_multi(self, Y):
+        """Y: n x ncomp (e.g. the PCA z-matrix): several training vectors on the same design."""
+        Y = _c(Y).reshape(self.n, -1)
+        _check(self.L.emub_model_set_training_multi(self.h, _P(Y), Y.shape[1], Y.shape[1]))
+        self.Y = Y
+        self.ncomp = Y.shape[1]
+
     def cov_matrix(self, thetas):
         C = np.empty((self.n, self.n))
         _check(self.L.emub_cov_matrix(self.h, _P(_c(thetas)), _P(C), self.n))
@@ -203,15 +216,20 @@ class Model:
         _check(self.L.emub_k_vectors(self.h, _P(_c(thetas)), _P(pts), self.d, pts.shape[0], _P(K), pts.shape[0]))
         return K
 
-    def loglik_grad_batch(self, thetas, want_grad=True):
-        """thetas: B x (nthetas-1).  Returns dict(negL[B], grad[B, nthetas-1], sigma2[B], status[B])."""
+    def loglik_grad_batch(self, thetas, want_grad=True, comp=None):
+        """thetas: B x (nthetas-1); comp: optional training-vector index per point.
+        Returns dict(negL[B], grad[B, nthetas-1], sigma2[B], status[B])."""
         th = _c(thetas).reshape(-1, self.nthetas - 1)
         B = th.shape[0]
         negL, s2 = np.empty(B), np.empty(B)
         grad = np.zeros((B, self.nthetas - 1))
         st = np.zeros(B, dtype=np.int32)
-        _check(self.L.emub_loglik_grad_batch(self.h, _P(th), B, 1 if want_grad else 0, _P(negL), _P(grad), _P(s2),
-                                             st.ctypes.data_as(_ip)))
+        cp = None
+        if comp is not None:
+            comp = np.ascontiguousarray(comp, dtype=np.int32)
+            cp = comp.ctypes.data_as(_ip)
+        _check(self.L.emub_loglik_grad_batch_comp(self.h, _P(th), cp, B, 1 if want_grad else 0, _P(negL), _P(grad), _P(s2),
+                                                  st.ctypes.data_as(_ip)))
         return dict(negL=negL, grad=grad, sigma2=s2, status=st)
 
     def loglik_grad(self, theta_less_amp, want_grad=True):
@@ -237,8 +255,8 @@ class Model:
             _check(rc)
         return rc, Lm, ld.value
 
-    def emulator(self, thetas):
-        return Emulator(self, thetas)
+    def emulator(self, thetas, comp=0):
+        return Emulator(self, thetas, comp)
 
     def close(self):
         if getattr(self, "h", None):
@@ -255,11 +273,11 @@ class Model:
 class Emulator:
     """Cached factor for prediction (emub_emulator; the reference's emulator_struct)."""
 
-    def __init__(self, model, thetas):
+    def __init__(self, model, thetas, comp=0):
         self.model = model
         self.L = model.L
         h = _vp()
-        _check(self.L.emub_emulator_create(model.h, _P(_c(thetas)), ctypes.byref(h)))
+        _check(self.L.emub_emulator_create_comp(model.h, comp, _P(_c(thetas)), ctypes.byref(h)))
         self.h = h
 
     def emulate(self, pts):
@@ -289,10 +307,30 @@ class Emulator:
             pass
 
 
+def predict_multi(emulators, pts, training_mean=None, evecs=None, evals=None):
+    """emulate_point_multi (multivar_support.c:103) for a block of points: emulators = the nr PCA-component
+    emulators of ONE model.  With the projection data returns (mean, var) of shape (m, nt) in observable space;
+    without it the PCA-space values (m, nr) (emulate_point_multi_pca)."""
+    model = emulators[0].model
+    pts = _c(pts).reshape(-1, model.d)
+    m, nr = pts.shape[0], len(emulators)
+    arr = (_vp * nr)(*[em.h for em in emulators])
+    if evecs is not None:
+        evecs = _c(evecs).reshape(-1, nr)
+        nt = evecs.shape[0]
+        mean, var = np.empty((m, nt)), np.empty((m, nt))
+        _check(model.L.emub_predict_multi(arr, nr, _P(pts), model.d, m, nt, _P(_c(training_mean)), _P(evecs), _P(_c(evals)),
+                                          _P(mean), _P(var)))
+    else:
+        mean, var = np.empty((m, nr)), np.empty((m, nr))
+        _check(model.L.emub_predict_multi(arr, nr, _P(pts), model.d, m, 0, None, None, None, _P(mean), _P(var)))
+    return mean, var
+
+
 # ---- host C layer (madaiemulator_b200/host/libemuhost.so): restart driver over the batched evaluator ----------
 HOST_LIB_PATH = os.path.join(_HERE, "host", "libemuhost.so")
 HOST_SYMBOLS = ["emub_estimate_default_opts", "emub_sample_scales", "emub_optimization_ranges", "emub_random_init",
-                "emub_estimate_thetas", "emub_estimate_thetas_from"]
+                "emub_estimate_thetas", "emub_estimate_thetas_from", "emub_estimate_thetas_multi"]
 
 
 class EstimateOpts(ctypes.Structure):
@@ -325,6 +363,7 @@ def host_lib():
     H.emub_random_init.restype = None
     H.emub_estimate_thetas.argtypes = [_vp, _dp, ctypes.POINTER(EstimateOpts), _dp, _dp, ctypes.POINTER(EstimateStats)]
     H.emub_estimate_thetas_from.argtypes = [_vp, _dp, _dp, ctypes.POINTER(EstimateOpts), _dp, _dp, ctypes.POINTER(EstimateStats)]
+    H.emub_estimate_thetas_multi.argtypes = [_vp, _ci, _dp, ctypes.POINTER(EstimateOpts), _dp, _dp, ctypes.POINTER(EstimateStats)]
     _hostlib = H
     return H
 
@@ -368,3 +407,23 @@ def estimate_thetas(model, ranges=None, max_tries=50, nchains=0, seed=1, starts=
         _check(rc)
     return th, best.value, dict(rc=rc, evaluations=st.evaluations, batches=st.batches, success_count=st.success_count,
                                 finite_count=st.finite_count)
+
+
+def estimate_thetas_multi(model, ncomp, ranges=None, max_tries=50, nchains=0, seed=1):
+    """estimate_multi (multivar_support.c:20) with the restart fronts of all ncomp components merged into one batch.
+    Returns (thetas[ncomp, nthetas], best log likelihoods[ncomp], stats)."""
+    H = host_lib()
+    if ranges is None:
+        ranges = optimization_ranges(model.kernel, model.X)
+    ranges = _c(ranges)
+    o = EstimateOpts()
+    H.emub_estimate_default_opts(ctypes.byref(o))
+    o.max_tries, o.nchains, o.seed = max_tries, nchains, seed
+    th = np.zeros((ncomp, model.nthetas))
+    best = np.zeros(ncomp)
+    st = EstimateStats()
+    rc = H.emub_estimate_thetas_multi(model.h, ncomp, _P(ranges), ctypes.byref(o), _P(th), _P(best), ctypes.byref(st))
+    if rc not in (OK, EDOM):
+        _check(rc)
+    return th, best, dict(rc=rc, evaluations=st.evaluations, batches=st.batches, success_count=st.success_count,
+                          finite_count=st.finite_count)

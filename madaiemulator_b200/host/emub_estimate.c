@@ -82,6 +82,9 @@ struct front;
 typedef struct {
 	struct front *fr;
 	int id;
+	int comp;             /* training vector (PCA component) this chain optimises */
+	int first_try, try_stride;
+	unsigned long long seed;
 	int state;
 	double *x, *g;        /* request point (nth1), returned gradient */
 	double f, sigma2;
@@ -160,7 +163,7 @@ static void run_restart(chain_t *c, int try_index, emub_bfgs *bf)
 	double *x_init = (double *)malloc(sizeof(double) * (size_t)nth);
 	double *x_final = (double *)malloc(sizeof(double) * (size_t)nth1);
 	if (fr->starts) memcpy(x_init, fr->starts + (size_t)try_index * nth, sizeof(double) * (size_t)nth);
-	else emub_random_init(o->seed, try_index, fr->ranges, nth, x_init);
+	else emub_random_init(c->seed, try_index, fr->ranges, nth, x_init);
 	emub_bfgs_fn fn = {(size_t)nth1, cb_f, cb_df, cb_fdf, c};
 	int status = emub_bfgs_set(bf, &fn, x_init + 1, o->step_size, o->tol); /* skip the amplitude, :665-668 */
 	int stepcount = 0;
@@ -192,7 +195,7 @@ static void *chain_main(void *arg)
 	chain_t *c = (chain_t *)arg;
 	front_t *fr = c->fr;
 	emub_bfgs *bf = emub_bfgs_alloc((size_t)fr->nth1);
-	for (int t = c->id; t < fr->opts->max_tries; t += fr->nchains) {
+	for (int t = c->first_try; t < fr->opts->max_tries; t += c->try_stride) {
 		c->cvalid = 0;
 		run_restart(c, t, bf);
 	}
@@ -204,6 +207,10 @@ static void *chain_main(void *arg)
 	return NULL;
 }
 
+static int estimate_impl(emub_model *model, int ncomp, const double *ranges, const double *starts,
+                         const emub_estimate_opts *opts_in, double *thetas_out, double *best_lhood,
+                         emub_estimate_stats *stats);
+
 int emub_estimate_thetas(emub_model *model, const double *ranges, const emub_estimate_opts *opts_in,
                          double *thetas_out, double *best_lhood, emub_estimate_stats *stats)
 {
@@ -214,12 +221,28 @@ int emub_estimate_thetas_from(emub_model *model, const double *ranges, const dou
                               const emub_estimate_opts *opts_in, double *thetas_out, double *best_lhood,
                               emub_estimate_stats *stats)
 {
+	return estimate_impl(model, 1, ranges, starts, opts_in, thetas_out, best_lhood, stats);
+}
+
+int emub_estimate_thetas_multi(emub_model *model, int ncomp, const double *ranges, const emub_estimate_opts *opts_in,
+                               double *thetas_out, double *best_lhood, emub_estimate_stats *stats)
+{
+	if (ncomp < 1 || ncomp > emub_model_ncomponents(model)) return EMUB_EINVAL;
+	return estimate_impl(model, ncomp, ranges, NULL, opts_in, thetas_out, best_lhood, stats);
+}
+
+/* ncomp components x nchains chains each, all in one evaluation front */
+static int estimate_impl(emub_model *model, int ncomp, const double *ranges, const double *starts,
+                         const emub_estimate_opts *opts_in, double *thetas_out, double *best_lhood,
+                         emub_estimate_stats *stats)
+{
 	if (!model || (!ranges && !starts) || !thetas_out) return EMUB_EINVAL;
 	emub_estimate_opts o;
 	if (opts_in) o = *opts_in; else emub_estimate_default_opts(&o);
 	if (o.max_tries < 1) o.max_tries = 1;
-	int nchains = o.nchains > 0 ? o.nchains : (o.max_tries < 64 ? o.max_tries : 64);
-	if (nchains > o.max_tries) nchains = o.max_tries;
+	int per_comp = o.nchains > 0 ? o.nchains : (o.max_tries < 64 ? o.max_tries : 64);
+	if (per_comp > o.max_tries) per_comp = o.max_tries;
+	int nchains = per_comp * ncomp;
 	front_t fr;
 	memset(&fr, 0, sizeof(fr));
 	fr.model = model; fr.opts = &o; fr.ranges = ranges; fr.starts = starts;
@@ -233,6 +256,8 @@ int emub_estimate_thetas_from(emub_model *model, const double *ranges, const dou
 	for (int i = 0; i < nchains; i++) {
 		chain_t *c = &fr.chains[i];
 		c->fr = &fr; c->id = i; c->best_lhood = SCREWUPVALUE;
+		c->comp = i / per_comp; c->first_try = i % per_comp; c->try_stride = per_comp;
+		c->seed = o.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)c->comp;
 		c->x = (double *)calloc(1, vb); c->g = (double *)calloc(1, vb);
 		c->cx = (double *)calloc(1, vb); c->cg = (double *)calloc(1, vb);
 		c->best_thetas = (double *)calloc(1, vb);
@@ -247,6 +272,7 @@ int emub_estimate_thetas_from(emub_model *model, const double *ranges, const dou
 	double *bs = (double *)malloc(sizeof(double) * (size_t)nchains);
 	int *bst = (int *)malloc(sizeof(int) * (size_t)nchains);
 	int *who = (int *)malloc(sizeof(int) * (size_t)nchains);
+	int *bcomp = (int *)malloc(sizeof(int) * (size_t)nchains);
 	int rc = EMUB_OK;
 	pthread_mutex_lock(&fr.mu);
 	for (;;) {
@@ -256,10 +282,11 @@ int emub_estimate_thetas_from(emub_model *model, const double *ranges, const dou
 		for (int i = 0; i < nchains; i++)
 			if (fr.chains[i].state == REQ_PENDING) {
 				memcpy(bx + (size_t)B * fr.nth1, fr.chains[i].x, sizeof(double) * (size_t)fr.nth1);
+				bcomp[B] = fr.chains[i].comp;
 				who[B++] = i;
 			}
 		pthread_mutex_unlock(&fr.mu);
-		int call = emub_loglik_grad_batch(model, bx, B, 1, bf, bg, bs, bst);
+		int call = emub_loglik_grad_batch_comp(model, bx, bcomp, B, 1, bf, bg, bs, bst);
 		pthread_mutex_lock(&fr.mu);
 		if (call != EMUB_OK) { rc = call; fr.failed = 1; }
 		fr.evaluations += B;
@@ -281,30 +308,32 @@ int emub_estimate_thetas_from(emub_model *model, const double *ranges, const dou
 	pthread_mutex_unlock(&fr.mu);
 	for (int i = 0; i < nchains; i++) pthread_join(tids[i], NULL);
 
-	/* global best over chains, in chain order (deterministic) -- estimate_threaded.c:294-323 */
-	double best = SCREWUPVALUE;
-	int succ = 0, fin = 0;
-	for (int i = 0; i < nchains; i++) {
-		chain_t *c = &fr.chains[i];
-		succ += c->success_count;
-		fin += c->finite_count;
-		if (c->best_lhood > best) {
-			best = c->best_lhood;
-			memcpy(thetas_out, c->best_thetas, vb);
+	/* best per component over its chains, in chain order (deterministic) -- estimate_threaded.c:294-323 */
+	int succ = 0, fin = 0, nfailed_comp = 0;
+	for (int k = 0; k < ncomp; k++) {
+		double best = SCREWUPVALUE;
+		for (int i = k * per_comp; i < (k + 1) * per_comp; i++) {
+			chain_t *c = &fr.chains[i];
+			succ += c->success_count;
+			fin += c->finite_count;
+			if (c->best_lhood > best) {
+				best = c->best_lhood;
+				memcpy(thetas_out + (size_t)k * fr.nth, c->best_thetas, vb);
+			}
+		}
+		if (best_lhood) best_lhood[k] = best;
+		if (best == SCREWUPVALUE) {
+			nfailed_comp++;
+			for (int i = 0; i < fr.nth; i++) thetas_out[(size_t)k * fr.nth + i] = 0.0;
 		}
 	}
-	if (best_lhood) *best_lhood = best;
 	if (stats) { stats->evaluations = fr.evaluations; stats->batches = fr.batches; stats->success_count = succ; stats->finite_count = fin; }
 	for (int i = 0; i < nchains; i++) {
 		chain_t *c = &fr.chains[i];
 		free(c->x); free(c->g); free(c->cx); free(c->cg); free(c->best_thetas);
 	}
-	free(fr.chains); free(tids); free(bx); free(bg); free(bf); free(bs); free(bst); free(who);
+	free(fr.chains); free(tids); free(bx); free(bg); free(bf); free(bs); free(bst); free(who); free(bcomp);
 	pthread_mutex_destroy(&fr.mu); pthread_cond_destroy(&fr.cv_disp); pthread_cond_destroy(&fr.cv_done);
 	if (rc != EMUB_OK) return rc;
-	if (best == SCREWUPVALUE) {
-		for (int i = 0; i < fr.nth; i++) thetas_out[i] = 0.0;
-		return EMUB_EDOM;
-	}
-	return EMUB_OK;
+	return nfailed_comp ? EMUB_EDOM : EMUB_OK;
 }

@@ -60,6 +60,16 @@ int emub_estimate_thetas_from(emub_model *model, const double *ranges, const dou
                               const emub_estimate_opts *opts, double *thetas_out, double *best_lhood,
                               emub_estimate_stats *stats);
 
+/*
+ * estimate_multi (multivar_support.c:20-27) without its serial loop over the PCA components: the model carries ncomp
+ * training vectors (emub_model_set_training_multi) and the restart chains of ALL components feed one evaluation
+ * front.  opts->max_tries and opts->nchains are per component.  thetas_out: ncomp x nthetas, best_lhood: ncomp.
+ * Component k uses the start-point stream seed + k * 0x9E3779B97F4A7C15, so its result equals a single-component run
+ * with that seed.
+ */
+int emub_estimate_thetas_multi(emub_model *model, int ncomp, const double *ranges, const emub_estimate_opts *opts,
+                               double *thetas_out, double *best_lhood, emub_estimate_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

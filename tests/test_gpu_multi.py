@@ -1,0 +1,113 @@
+"""GPU: the component-batched callers: estimate_multi / alloc_multi_emulator / emulate_point_multi
+re-expressed over the batched C-ABI -- all PCA components of a multivariate model share one design, one evaluation
+front and one prediction pass, with the back-projection on the device."""
+import os
+
+import numpy as np
+import pytest
+
+from madaiemulator_b200 import datasets as ds
+from tests.helpers import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+MULTI_SIMPLE = "/root/reference/test/multi-simple/multi-test-input.dat"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from madaiemulator_b200 import engine
+    c = engine.Context(0)
+    yield c
+    c.close()
+
+
+def _multi_problem(n=150, d=3, nt=6):
+    X, Y = ds.synthetic_model(n, d, nt)
+    pca = ds.pca_decompose(Y, 0.99)
+    return X, Y, pca
+
+
+def test_component_batch_equals_single_component_models(ctx):
+    from madaiemulator_b200 import engine
+    X, Y, pca = _multi_problem()
+    Z, nr = pca["Z"], pca["nr"]
+    assert nr >= 2
+    m = engine.Model(ctx, X, Z[:, 0], 1, 1, max_slots=8)
+    m.set_training_multi(Z)
+    rng = np.random.default_rng(0)
+    B = 11
+    ths = np.stack([np.concatenate([[rng.uniform(-5, -2)], rng.uniform(0.0, 1.5, X.shape[1])]) for _ in range(B)])
+    comp = rng.integers(0, nr, B)
+    r = m.loglik_grad_batch(ths, comp=comp)
+    for c in range(nr):
+        single = engine.Model(ctx, X, Z[:, c], 1, 1, max_slots=8)
+        idx = np.where(comp == c)[0]
+        if len(idx):
+            rs = single.loglik_grad_batch(ths[idx])
+            assert np.array_equal(rs["negL"], r["negL"][idx]) and np.array_equal(rs["grad"], r["grad"][idx])
+            assert np.array_equal(rs["sigma2"], r["sigma2"][idx])
+        single.close()
+    # and against the CPU oracle
+    from oracle.pyoracle import PortOracle
+    for b in (0, B - 1):
+        ref = PortOracle(X, Z[:, comp[b]], 1, 1).loglik_grad(ths[b])
+        assert relerr(r["negL"][b], ref["negL"]) < TOL
+    m.close()
+
+
+def test_predict_multi_matches_oracle_backprojection(ctx):
+    """emulate_point_multi: per-component emulators + back-projection (multivar_support.c:126-151)."""
+    from madaiemulator_b200 import engine
+    from oracle.pyoracle import PortOracle, backproject
+    X, Y, pca = _multi_problem()
+    Z, nr, nt = pca["Z"], pca["nr"], Y.shape[1]
+    d = X.shape[1]
+    m = engine.Model(ctx, X, Z[:, 0], 1, 1, max_slots=4)
+    m.set_training_multi(Z)
+    rng = np.random.default_rng(1)
+    thetas = np.stack([np.concatenate([[rng.uniform(-1, 0.5), rng.uniform(-5, -3)], rng.uniform(0.3, 1.2, d)]) for _ in range(nr)])
+    emus = [m.emulator(thetas[c], comp=c) for c in range(nr)]
+    pts = ds.synthetic_queries(300, d)
+    pts[0] = X[7]
+    mean, var = engine.predict_multi(emus, pts, pca["mean"], pca["evecs"], pca["evals"])
+    mp, vp = engine.predict_multi(emus, pts)
+    assert mean.shape == (300, nt) and mp.shape == (300, nr)
+    om = np.empty((300, nr))
+    ov = np.empty((300, nr))
+    for c in range(nr):
+        om[:, c], ov[:, c] = PortOracle(X, Z[:, c], 1, 1).emulator(thetas[c]).emulate(pts)
+    assert relerr(mp, om, 1e-3) < TOL
+    assert np.max(np.abs(vp - ov)) < TOL * 2.0
+    for q in (0, 1, 150, 299):
+        mo, vo = backproject(pca["mean"], pca["evecs"], pca["evals"], om[q], ov[q])
+        assert np.max(np.abs(mean[q] - mo)) < TOL * max(1.0, np.max(np.abs(mo)))
+        assert np.max(np.abs(var[q] - vo)) < TOL * max(1.0, np.max(np.abs(vo)))
+    for e in emus:
+        e.close()
+    m.close()
+
+
+def test_estimate_multi_merges_fronts(ctx):
+    """All components' restart chains in one evaluation front; component k's result equals a single-component run."""
+    from madaiemulator_b200 import engine
+    X, Y, pca = _multi_problem(n=100)
+    Z, nr = pca["Z"], pca["nr"]
+    m = engine.Model(ctx, X, Z[:, 0], 1, 0, max_slots=32)
+    m.set_training_multi(Z)
+    th, best, st = engine.estimate_thetas_multi(m, nr, max_tries=6, nchains=6, seed=3)
+    assert st["rc"] == 0 and np.all(np.isfinite(best))
+    assert st["evaluations"] / st["batches"] > 6  # wider than any single component's front
+    k = nr - 1
+    single = engine.Model(ctx, X, Z[:, k], 1, 0, max_slots=8)
+    th1, best1, _ = engine.estimate_thetas(single, max_tries=6, nchains=6, seed=(3 + 0x9E3779B97F4A7C15 * k) % (1 << 64))
+    assert np.array_equal(th1, th[k]) and best1 == best[k]
+    single.close()
+    m.close()
+
+
+@pytest.mark.skipif(not os.path.exists(MULTI_SIMPLE), reason="reference fixture not on this machine")
+def test_multi_simple_fixture_shape():
+    X, Y = ds.load_input_model_file(MULTI_SIMPLE)
+    assert X.shape == (100, 3) and Y.shape == (100, 6)
+    assert ds.pca_decompose(Y, 0.99)["nr"] <= 5
