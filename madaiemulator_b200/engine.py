@@ -330,7 +330,9 @@ def predict_multi(emulators, pts, training_mean=None, evecs=None, evals=None):
 # ---- host C layer (madaiemulator_b200/host/libemuhost.so): restart driver over the batched evaluator ----------
 HOST_LIB_PATH = os.path.join(_HERE, "host", "libemuhost.so")
 HOST_SYMBOLS = ["emub_estimate_default_opts", "emub_sample_scales", "emub_optimization_ranges", "emub_random_init",
-                "emub_estimate_thetas", "emub_estimate_thetas_from", "emub_estimate_thetas_multi"]
+                "emub_estimate_thetas", "emub_estimate_thetas_from", "emub_estimate_thetas_multi", "emub_snapshot_load",
+                "emub_snapshot_load_path", "emub_snapshot_free", "emub_multi_emulator_from_snapshot",
+                "emub_multi_emulator_destroy", "emub_multi_emulator_predict", "emub_interactive_stream"]
 
 
 class EstimateOpts(ctypes.Structure):

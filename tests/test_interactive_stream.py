@@ -1,0 +1,135 @@
+"""MODEL_SNAPSHOT_FILE reader and the streaming interactive_mode, against fixtures produced by
+the reference's own CLI (tests/golden/cli/README.md)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI_DIR = os.path.join(ROOT, "tests", "golden", "cli")
+TOOL = os.path.join(ROOT, "madaiemulator_b200", "host", "emub_interactive_emulator")
+DROPIN_CLI = os.path.join(ROOT, "oracle", "_ref", "interactive_emulator_dropin")
+
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+class _Comp(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int) for k in ("nthetas", "nparams", "nmodel_points", "nemulate_points", "regression_order",
+                                            "nregression_fns", "fixed_nugget_mode", "cov_fn_index", "use_data_scales")] + \
+               [("fixed_nugget", ctypes.c_double)] + [(k, _dp) for k in ("grad_ranges", "xmodel", "training_vector", "thetas", "sample_scales")]
+
+
+class _Snap(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int) for k in ("nt", "nr", "nparams", "nmodel_points", "cov_fn_index", "regression_order")] + \
+               [(k, _dp) for k in ("xmodel", "training_matrix", "training_mean", "pca_evals_r", "pca_evecs_r", "pca_zmatrix")] + \
+               [("components", ctypes.POINTER(_Comp))]
+
+
+def _tokens(path):
+    return open(path).read().split()
+
+
+@pytest.mark.parametrize("name,nt,nr,d,n,order", [("uni-simple-o1", 1, 1, 1, 34, 1), ("multi-simple-o0", 6, 5, 3, 100, 0)])
+def test_snapshot_reader(name, nt, nr, d, n, order):
+    from madaiemulator_b200 import engine
+    H = engine.host_lib()
+    H.emub_snapshot_load_path.restype = ctypes.POINTER(_Snap)
+    H.emub_snapshot_load_path.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    H.emub_snapshot_free.argtypes = [ctypes.POINTER(_Snap)]
+    H.emub_snapshot_free.restype = None
+    path = os.path.join(CLI_DIR, name + ".snapshot")
+    err = ctypes.create_string_buffer(256)
+    sp = H.emub_snapshot_load_path(path.encode(), err, 256)
+    assert sp, err.value
+    s = sp.contents
+    assert (s.nt, s.nr, s.nparams, s.nmodel_points, s.cov_fn_index, s.regression_order) == (nt, nr, d, n, 1, order)
+    tok = _tokens(path)
+    X = np.array(tok[6:6 + n * d], dtype=np.float64)
+    assert np.array_equal(np.ctypeslib.as_array(s.xmodel, (n * d,)), X)
+    Y = np.array(tok[6 + n * d:6 + n * d + n * nt], dtype=np.float64).reshape(n, nt)
+    assert np.array_equal(np.ctypeslib.as_array(s.training_matrix, (n * nt,)), Y.ravel())
+    mean = np.ctypeslib.as_array(s.training_mean, (nt,))
+    assert np.allclose(mean, Y.mean(axis=0), rtol=1e-14, atol=1e-15)
+    # the last component block ends the file: its sample scales are the last d tokens, its thetas the nthetas before
+    last = s.components[nr - 1]
+    assert last.nthetas == d + 2 and last.regression_order == order and last.nregression_fns == 1 + order * d
+    assert np.array_equal(np.ctypeslib.as_array(last.sample_scales, (d,)), np.array(tok[-d:], dtype=np.float64))
+    assert np.array_equal(np.ctypeslib.as_array(last.thetas, (d + 2,)), np.array(tok[-d - (d + 2):-d], dtype=np.float64))
+    # every block repeats the design, and its training vector is the matching z-matrix column
+    Z = np.ctypeslib.as_array(s.pca_zmatrix, (n * nr,)).reshape(n, nr)
+    for c in range(nr):
+        comp = s.components[c]
+        assert np.array_equal(np.ctypeslib.as_array(comp.xmodel, (n * d,)), X)
+        assert np.array_equal(np.ctypeslib.as_array(comp.training_vector, (n,)), Z[:, c])
+    H.emub_snapshot_free(sp)
+    # malformed input is reported, not crashed on
+    bad = os.path.join("/tmp", "bad_%s.snapshot" % name)
+    open(bad, "w").write(" ".join(tok[:50]))
+    assert not H.emub_snapshot_load_path(bad.encode(), err, 256)
+    assert b"malformed" in err.value
+
+
+def _compare_protocol(out_text, golden_path, nt, nheader, nr=None):
+    got = out_text.split("\n")
+    ref = open(golden_path).read().split("\n")
+    assert len(got) == len(ref)
+    assert got[:nheader] == ref[:nheader]  # header lines are byte-identical
+    g = np.array(got[nheader:-1], dtype=np.float64).reshape(-1, nt, 2)
+    r = np.array(ref[nheader:-1], dtype=np.float64).reshape(-1, nt, 2)
+    if nr is not None:  # --pca_output: only the first nr entries are meaningful (interactive_emulator.c:426-429)
+        g, r = g[:, :nr], r[:, :nr]
+    assert np.max(np.abs(g[..., 0] - r[..., 0]) / np.maximum(1.0, np.abs(r[..., 0]))) < 1e-9
+    assert np.max(np.abs(g[..., 1] - r[..., 1])) < 1e-9 * max(1.0, np.max(np.abs(r[..., 1])))
+    # same text format: 17 digits after the point
+    assert all(len(x.split(".")[1]) == 17 for x in got[nheader:nheader + 20])
+
+
+@pytest.mark.gpu
+def test_streaming_interactive_mode_matches_reference_cli():
+    assert os.path.exists(TOOL), "run make -C madaiemulator_b200/host"
+    for name, pts, nt, d in (("uni-simple-o1", "uni-simple.points", 1, 1), ("multi-simple-o0", "multi-simple.points", 6, 3)):
+        snap = os.path.join(CLI_DIR, name + ".snapshot")
+        inp = open(os.path.join(CLI_DIR, pts), "rb").read()
+        out = subprocess.run([TOOL, "interactive_mode", snap], input=inp, capture_output=True, check=True, timeout=300).stdout.decode()
+        _compare_protocol(out, os.path.join(CLI_DIR, name + ".interactive.txt"), nt, 1 + d + 1 + 2 * nt)
+    snap = os.path.join(CLI_DIR, "multi-simple-o0.snapshot")
+    inp = open(os.path.join(CLI_DIR, "multi-simple.points"), "rb").read()
+    out = subprocess.run([TOOL, "interactive_mode", snap, "--quiet"], input=inp, capture_output=True, check=True, timeout=300).stdout.decode()
+    _compare_protocol(out, os.path.join(CLI_DIR, "multi-simple-o0.interactive_quiet.txt"), 6, 0)
+    out = subprocess.run([TOOL, "interactive_mode", snap, "--pca_output"], input=inp, capture_output=True, check=True, timeout=300).stdout.decode()
+    _compare_protocol(out, os.path.join(CLI_DIR, "multi-simple-o0.interactive_pca.txt"), 6, 0, nr=5)
+    # tiny blocks give the same bytes as one big block
+    small = subprocess.run([TOOL, "interactive_mode", snap, "--quiet", "--block", "7"], input=inp, capture_output=True, check=True, timeout=300).stdout.decode()
+    big = subprocess.run([TOOL, "interactive_mode", snap, "--quiet"], input=inp, capture_output=True, check=True, timeout=300).stdout.decode()
+    assert small == big
+
+
+@pytest.mark.gpu
+def test_request_response_client_is_served_point_by_point():
+    """A client that writes one point and waits for its 2*nt answer lines (the reference flushes per point) must not
+    dead-lock on the block reader."""
+    snap = os.path.join(CLI_DIR, "multi-simple-o0.snapshot")
+    p = subprocess.Popen([TOOL, "interactive_mode", snap, "--quiet"], stdin=subprocess.PIPE, stdout=subprocess.PIPE)
+    ref = open(os.path.join(CLI_DIR, "multi-simple-o0.interactive_quiet.txt")).read().split("\n")
+    pts = open(os.path.join(CLI_DIR, "multi-simple.points")).read().split("\n")
+    for q in range(3):
+        p.stdin.write((pts[q] + "\n").encode())
+        p.stdin.flush()
+        lines = [p.stdout.readline().decode().strip() for _ in range(12)]
+        vals = np.array(lines, dtype=np.float64)
+        assert np.max(np.abs(vals - np.array(ref[12 * q:12 * q + 12], dtype=np.float64))) < 1e-9
+    p.stdin.close()
+    assert p.wait(timeout=60) == 0
+
+
+@pytest.mark.gpu
+def test_reference_cli_on_the_engine():
+    """The reference's own interactive_emulator.c, unmodified, linked with integration/libemu_glue.c."""
+    if not os.path.exists(DROPIN_CLI):
+        pytest.skip("oracle/_ref/interactive_emulator_dropin not built")
+    snap = os.path.join(CLI_DIR, "multi-simple-o0.snapshot")
+    inp = open(os.path.join(CLI_DIR, "multi-simple.points"), "rb").read()
+    out = subprocess.run([DROPIN_CLI, "interactive_mode", snap], input=inp, capture_output=True, check=True, timeout=300).stdout.decode()
+    _compare_protocol(out, os.path.join(CLI_DIR, "multi-simple-o0.interactive.txt"), 6, 1 + 3 + 1 + 12)
