@@ -33,9 +33,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="theta points per step per GPU")
+    ap.add_argument("--batch", type=int, default=64, help="theta points per step per GPU (BASELINE cfg3: 64 restarts batched)")
     ap.add_argument("--pred-points", type=int, default=1 << 18, help="query points per prediction step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--groups", type=int, default=0, help="stream groups (0 = min(4, batch/4))")
     return ap.parse_args()
 
 
@@ -212,7 +213,7 @@ def main():
     nth1 = D_MODEL + 1
 
     ctx = engine.Context(local)
-    ctx.set_groups(min(4, max(1, B // 4)))
+    ctx.set_groups(args.groups if args.groups > 0 else min(4, max(1, B // 4)))
     model = engine.Model(ctx, X, y, engine.POWEREXP, ORDER, max_slots=B)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     d_thetas = torch.tensor(thetas, dtype=torch.float64, device="cuda").contiguous()
