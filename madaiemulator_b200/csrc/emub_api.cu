@@ -886,7 +886,7 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 	launch_kcross(m, st, e->consts, dQ, mq, mq_pad, w->dK, ldk);
 	const int nqb = mq_pad / TB;
 	// |W k|^2 partials: tile (row block i, query block qb)
-	launch_gemm<KMAJOR, RMAJOR, EPI_COLSUMSQ>(c, EMUB_K_GEMM_PRED, (double)m->npad * (m->npad + TB / 2) * TB, st, w->dTasks, m->nblk, nqb,
+	launch_gemm<KMAJOR, RMAJOR, EPI_COLSUMSQ>(c, EMUB_K_GEMM_PRED, (double)m->npad * (m->npad + TB / 4) * TB, st, w->dTasks, m->nblk, nqb,
 	                                          e->W, 0, m->npad, w->dK, TB, ldk, w->dVsq, TB, ldk, 1.0);
 	{
 		const int nchunk_cols = (m->p + 1 + 7) / 8;

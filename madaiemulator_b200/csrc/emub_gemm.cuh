@@ -118,8 +118,11 @@ __device__ __forceinline__ double frag(const double *s, int r, int k)
 
 // acc[mi][ni][4]: warp tile WTM (m) x WTN (n)
 template <class Cfg, int AL, int BL>
+// [w_lo, w_hi): k-tiles for which THIS warp issues DMMAs (warp-uniform).  Outside it the warp still takes part in
+// the loads and barriers; its operands there are structural zeros of a triangular block.
 __device__ __forceinline__ void gemm_mainloop(const double *__restrict__ gA, const double *__restrict__ gB, int lda,
-                                              int ldb, int klen, double *smem, double (&acc)[Cfg::MI][Cfg::NI][4])
+                                              int ldb, int klen, int w_lo, int w_hi, double *smem,
+                                              double (&acc)[Cfg::MI][Cfg::NI][4])
 {
 	constexpr int BK = Cfg::BK, STAGES = Cfg::STAGES, STG = Cfg::STAGE_DOUBLES;
 	const int tid = threadIdx.x;
@@ -150,6 +153,7 @@ __device__ __forceinline__ void gemm_mainloop(const double *__restrict__ gA, con
 			}
 			cp_async_commit();
 		}
+		if (kt < w_lo || kt >= w_hi) continue;
 		const double *sA = smem + (kt % STAGES) * STG;
 		const double *sB = sA + Cfg::A_DOUBLES;
 #pragma unroll
@@ -183,18 +187,25 @@ constexpr int TASK_TRIM_BEGIN_SR1 = 1 << 26;
 constexpr int TASK_FLAGS = TASK_LOWER | TASK_TRIM_END_SC0 | TASK_TRIM_BEGIN_SC1 | TASK_TRIM_END_SR0 | TASK_TRIM_BEGIN_SR1;
 
 // executed flops of one task under the default 64 x 64 sub-tiling (host side bookkeeping)
-inline double task_flops(const GemmTask &t)
+inline double task_flops(const GemmTask &t, bool colsumsq = false)
 {
 	double f = 0.0;
 	for (int sr = 0; sr < 2; sr++)
 		for (int sc = 0; sc < 2; sc++) {
-			if ((t.aux & TASK_LOWER) && sc > sr) continue;
+			if (!colsumsq && (t.aux & TASK_LOWER) && sc > sr) continue;
 			int k = t.klen;
 			if ((t.aux & TASK_TRIM_END_SC0) && sc == 0) k -= 64;
 			if ((t.aux & TASK_TRIM_BEGIN_SC1) && sc == 1) k -= 64;
 			if ((t.aux & TASK_TRIM_END_SR0) && sr == 0) k -= 64;
 			if ((t.aux & TASK_TRIM_BEGIN_SR1) && sr == 1) k -= 64;
-			f += 2.0 * 64 * 64 * (double)k;
+			for (int wr = 0; wr < 2; wr++)
+				for (int wc = 0; wc < 2; wc++) {
+					int kw = k;
+					if (((t.aux & TASK_TRIM_END_SC0) && wc == 0) || ((t.aux & TASK_TRIM_END_SR0) && wr == 0)) kw -= 32;
+					if (((t.aux & TASK_TRIM_BEGIN_SC1) && wc == 1) || ((t.aux & TASK_TRIM_BEGIN_SR1) && wr == 1)) kw -= 32;
+					if (!colsumsq && (t.aux & TASK_LOWER) && sr == sc && wr == 0 && wc == 1) kw = 0;
+					f += 2.0 * 32 * 32 * (double)(kw > 0 ? kw : 0);
+				}
 		}
 	return f;
 }
@@ -231,7 +242,17 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) k_gemm(GemmArgs p)
 #pragma unroll
 			for (int r = 0; r < 4; r++) acc[i][j][r] = 0.0;
 
-	gemm_mainloop<Cfg, AL, BL>(gA, gB, p.lda, p.ldb, klen, smem, acc);
+	// warp-level window: a 32-row / 32-column warp tile needs even less of a triangular diagonal block
+	int w_lo = 0, w_hi = klen / Cfg::BK;
+	if (Cfg::BM == 64 && Cfg::BN == 64 && Cfg::WTM == 32 && Cfg::WTN == 32) {
+		const int w = threadIdx.x >> 5;
+		const int wr = w / Cfg::WN, wc = w % Cfg::WN;
+		constexpr int T32 = 32 / Cfg::BK;
+		if (((task.aux & TASK_TRIM_END_SC0) && wc == 0) || ((task.aux & TASK_TRIM_END_SR0) && wr == 0)) w_hi -= T32;
+		if (((task.aux & TASK_TRIM_BEGIN_SC1) && wc == 1) || ((task.aux & TASK_TRIM_BEGIN_SR1) && wr == 1)) w_lo += T32;
+		if (EPI != EPI_COLSUMSQ && (task.aux & TASK_LOWER) && sr == sc && wr == 0 && wc == 1) w_hi = 0;  // strictly upper warp tile
+	}
+	gemm_mainloop<Cfg, AL, BL>(gA, gB, p.lda, p.ldb, klen, w_lo, w_hi, smem, acc);
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
