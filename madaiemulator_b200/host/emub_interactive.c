@@ -1,6 +1,7 @@
 /* emub_interactive.c -- see emub_interactive.h.  Citations are file:line under the reference's src/. */
 #include "emub_interactive.h"
 #include <poll.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
@@ -10,6 +11,11 @@ struct emub_multi_emulator {
 	emub_emulator **emus;
 	int nt, nr, d;
 	double *training_mean, *evecs, *evals;
+	/* replicas on further devices (query blocks are independent: SURVEY 8e); replica 0 is this struct */
+	int nreplicas;
+	struct emub_multi_emulator **replicas; /* [nreplicas - 1] */
+	emub_ctx **owned_ctx;                  /* contexts created by _from_snapshot_devices */
+	int nowned;
 };
 
 int emub_multi_emulator_from_snapshot(emub_ctx *ctx, const emub_snapshot *s, emub_multi_emulator **out)
@@ -43,23 +49,87 @@ int emub_multi_emulator_from_snapshot(emub_ctx *ctx, const emub_snapshot *s, emu
 	return EMUB_OK;
 }
 
+int emub_multi_emulator_from_snapshot_devices(const int *devices, int ndev, const emub_snapshot *s, emub_multi_emulator **out)
+{
+	if (!devices || ndev < 1 || !s || !out) return EMUB_EINVAL;
+	emub_ctx **ctxs = (emub_ctx **)calloc((size_t)ndev, sizeof(emub_ctx *));
+	emub_multi_emulator **mes = (emub_multi_emulator **)calloc((size_t)ndev, sizeof(emub_multi_emulator *));
+	int rc = EMUB_OK;
+	for (int g = 0; g < ndev && rc == EMUB_OK; g++) {
+		rc = emub_ctx_create(devices[g], &ctxs[g]);
+		if (rc == EMUB_OK) rc = emub_multi_emulator_from_snapshot(ctxs[g], s, &mes[g]);
+	}
+	if (rc != EMUB_OK) {
+		for (int g = 0; g < ndev; g++) { emub_multi_emulator_destroy(mes[g]); if (ctxs[g]) emub_ctx_destroy(ctxs[g]); }
+		free(ctxs); free(mes);
+		return rc;
+	}
+	emub_multi_emulator *me = mes[0];
+	me->nreplicas = ndev;
+	me->replicas = (emub_multi_emulator **)calloc((size_t)ndev, sizeof(emub_multi_emulator *));
+	for (int g = 1; g < ndev; g++) me->replicas[g - 1] = mes[g];
+	me->owned_ctx = ctxs;
+	me->nowned = ndev;
+	free(mes);
+	*out = me;
+	return EMUB_OK;
+}
+
 void emub_multi_emulator_destroy(emub_multi_emulator *me)
 {
 	if (!me) return;
+	for (int g = 1; g < me->nreplicas; g++) emub_multi_emulator_destroy(me->replicas[g - 1]);
+	free(me->replicas);
+	emub_ctx **owned = me->owned_ctx;
+	const int nowned = me->nowned;
 	if (me->emus)
 		for (int c = 0; c < me->nr; c++) emub_emulator_destroy(me->emus[c]);
 	free(me->emus);
 	emub_model_destroy(me->model);
 	free(me->training_mean); free(me->evecs); free(me->evals);
 	free(me);
+	for (int g = 0; g < nowned; g++) emub_ctx_destroy(owned[g]);
+	free(owned);
 }
 int emub_multi_emulator_nt(const emub_multi_emulator *me) { return me ? me->nt : 0; }
 int emub_multi_emulator_nr(const emub_multi_emulator *me) { return me ? me->nr : 0; }
 int emub_multi_emulator_nparams(const emub_multi_emulator *me) { return me ? me->d : 0; }
 
+static int predict_one(emub_multi_emulator *me, const double *pts, int m, int pca_output, double *mean, double *var);
+
+typedef struct { emub_multi_emulator *me; const double *pts; int m, pca; double *mean, *var; int rc; } shard_job;
+static void *shard_main(void *arg)
+{
+	shard_job *j = (shard_job *)arg;
+	j->rc = predict_one(j->me, j->pts, j->m, j->pca, j->mean, j->var);
+	return NULL;
+}
+
+/* contiguous blocks of the query list, one per device replica, run concurrently (one host thread per GPU) */
 int emub_multi_emulator_predict(emub_multi_emulator *me, const double *pts, int m, int pca_output, double *mean, double *var)
 {
 	if (!me || !pts || !mean || !var || m < 0) return EMUB_EINVAL;
+	const int G = me->nreplicas > 1 ? me->nreplicas : 1;
+	if (G == 1 || m < 2 * G) return predict_one(me, pts, m, pca_output, mean, var);
+	shard_job jobs[64];
+	pthread_t th[64];
+	const int base = m / G, rem = m % G;
+	int lo = 0;
+	for (int g = 0; g < G; g++) {
+		const int cnt = base + (g < rem ? 1 : 0);
+		jobs[g].me = g == 0 ? me : me->replicas[g - 1];
+		jobs[g].pts = pts + (size_t)lo * me->d; jobs[g].m = cnt; jobs[g].pca = pca_output;
+		jobs[g].mean = mean + (size_t)lo * me->nt; jobs[g].var = var + (size_t)lo * me->nt; jobs[g].rc = EMUB_OK;
+		lo += cnt;
+		pthread_create(&th[g], NULL, shard_main, &jobs[g]);
+	}
+	int rc = EMUB_OK;
+	for (int g = 0; g < G; g++) { pthread_join(th[g], NULL); if (jobs[g].rc != EMUB_OK) rc = jobs[g].rc; }
+	return rc;
+}
+
+static int predict_one(emub_multi_emulator *me, const double *pts, int m, int pca_output, double *mean, double *var)
+{
 	if (!pca_output)
 		return emub_predict_multi(me->emus, me->nr, pts, me->d, m, me->nt, me->training_mean, me->evecs, me->evals, mean, var);
 	/* PCA space (multivar_support.c:78-101): nr values per point, laid out in rows of nt like the reference's vectors */
@@ -103,7 +173,7 @@ int emub_interactive_stream(emub_multi_emulator *me, FILE *in, FILE *out, int qu
 {
 	if (!me || !in || !out) return EMUB_EINVAL;
 	const int d = me->d, nt = me->nt;
-	if (block_points <= 0) block_points = 16384;
+	if (block_points <= 0) block_points = 16384 * (me->nreplicas > 1 ? me->nreplicas : 1);
 	long long total = 0;
 	if (!quiet) { /* interactive_emulator.c:398-414 */
 		fprintf(out, "%d\n", d);

@@ -20,6 +20,10 @@ typedef struct emub_multi_emulator emub_multi_emulator;
 /* alloc_multi_emulator (multivar_support.c:30-60) from a loaded snapshot: one model carrying the nr component
  * training vectors, one cached factor per component */
 int emub_multi_emulator_from_snapshot(emub_ctx *ctx, const emub_snapshot *s, emub_multi_emulator **out);
+/* the same on several GPUs of one box: one context + replica per device; emub_multi_emulator_predict (and therefore
+ * emub_interactive_stream) then splits every block of query points into contiguous shares, one host thread per
+ * device, no exchange between devices (query points are independent).  ndev <= 64. */
+int emub_multi_emulator_from_snapshot_devices(const int *devices, int ndev, const emub_snapshot *s, emub_multi_emulator **out);
 void emub_multi_emulator_destroy(emub_multi_emulator *me);
 int emub_multi_emulator_nt(const emub_multi_emulator *me);
 int emub_multi_emulator_nr(const emub_multi_emulator *me);

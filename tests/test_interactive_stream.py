@@ -133,3 +133,17 @@ def test_reference_cli_on_the_engine():
     inp = open(os.path.join(CLI_DIR, "multi-simple.points"), "rb").read()
     out = subprocess.run([DROPIN_CLI, "interactive_mode", snap], input=inp, capture_output=True, check=True, timeout=300).stdout.decode()
     _compare_protocol(out, os.path.join(CLI_DIR, "multi-simple-o0.interactive.txt"), 6, 1 + 3 + 1 + 12)
+
+
+@pytest.mark.gpu
+def test_query_blocks_shard_over_two_gpus():
+    """Query points are independent: with --devices 0,1 every block is split between two device
+    replicas (one host thread per GPU) and the output is byte-identical to the single-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    snap = os.path.join(CLI_DIR, "multi-simple-o0.snapshot")
+    inp = open(os.path.join(CLI_DIR, "multi-simple.points"), "rb").read()
+    one = subprocess.run([TOOL, "interactive_mode", snap, "--quiet"], input=inp, capture_output=True, check=True, timeout=300).stdout
+    two = subprocess.run([TOOL, "interactive_mode", snap, "--quiet", "--devices", "0,1"], input=inp, capture_output=True, check=True, timeout=300).stdout
+    assert one == two
