@@ -330,14 +330,15 @@ def predict_multi(emulators, pts, training_mean=None, evecs=None, evals=None):
 # ---- host C layer (madaiemulator_b200/host/libemuhost.so): restart driver over the batched evaluator ----------
 HOST_LIB_PATH = os.path.join(_HERE, "host", "libemuhost.so")
 HOST_SYMBOLS = ["emub_estimate_default_opts", "emub_sample_scales", "emub_optimization_ranges", "emub_random_init",
-                "emub_estimate_thetas", "emub_estimate_thetas_from", "emub_estimate_thetas_multi", "emub_snapshot_load",
+                "emub_estimate_thetas", "emub_estimate_thetas_from", "emub_estimate_thetas_multi", "emub_estimate_thetas_multi_devices", "emub_snapshot_load",
                 "emub_snapshot_load_path", "emub_snapshot_free", "emub_multi_emulator_from_snapshot",
                 "emub_multi_emulator_destroy", "emub_multi_emulator_predict", "emub_interactive_stream"]
 
 
 class EstimateOpts(ctypes.Structure):
     _fields_ = [("max_tries", _ci), ("nchains", _ci), ("seed", ctypes.c_ulonglong), ("step_size", ctypes.c_double),
-                ("tol", ctypes.c_double), ("eps_abs", ctypes.c_double), ("step_max", _ci)]
+                ("tol", ctypes.c_double), ("eps_abs", ctypes.c_double), ("step_max", _ci), ("first_component", _ci),
+                ("component_stride", _ci)]
 
 
 class EstimateStats(ctypes.Structure):
@@ -366,6 +367,8 @@ def host_lib():
     H.emub_estimate_thetas.argtypes = [_vp, _dp, ctypes.POINTER(EstimateOpts), _dp, _dp, ctypes.POINTER(EstimateStats)]
     H.emub_estimate_thetas_from.argtypes = [_vp, _dp, _dp, ctypes.POINTER(EstimateOpts), _dp, _dp, ctypes.POINTER(EstimateStats)]
     H.emub_estimate_thetas_multi.argtypes = [_vp, _ci, _dp, ctypes.POINTER(EstimateOpts), _dp, _dp, ctypes.POINTER(EstimateStats)]
+    H.emub_estimate_thetas_multi_devices.argtypes = [_ip, _ci, _dp, _ci, _ci, _ci, _dp, _ci, _ci, _ci, _ci, _ci,
+                                                     ctypes.POINTER(EstimateOpts), _dp, _dp, ctypes.POINTER(EstimateStats)]
     _hostlib = H
     return H
 
@@ -425,6 +428,29 @@ def estimate_thetas_multi(model, ncomp, ranges=None, max_tries=50, nchains=0, se
     best = np.zeros(ncomp)
     st = EstimateStats()
     rc = H.emub_estimate_thetas_multi(model.h, ncomp, _P(ranges), ctypes.byref(o), _P(th), _P(best), ctypes.byref(st))
+    if rc not in (OK, EDOM):
+        _check(rc)
+    return th, best, dict(rc=rc, evaluations=st.evaluations, batches=st.batches, success_count=st.success_count,
+                          finite_count=st.finite_count)
+
+
+def estimate_thetas_multi_devices(devices, X, Z, kernel=POWEREXP, order=0, max_tries=50, nchains=0, seed=1, max_slots=0):
+    """estimate_multi with the PCA components sharded over several GPUs of one box (component c -> devices[c % ndev]),
+    one host thread per device, no exchange between devices.  Returns (thetas[ncomp, nthetas], best[ncomp], stats)."""
+    H = host_lib()
+    X, Z = _c(X), _c(Z)
+    n, d = X.shape
+    ncomp = Z.shape[1]
+    nth = d + 2 if kernel == POWEREXP else 3
+    dev = np.ascontiguousarray(devices, dtype=np.int32)
+    o = EstimateOpts()
+    H.emub_estimate_default_opts(ctypes.byref(o))
+    o.max_tries, o.nchains, o.seed = max_tries, nchains, seed
+    th = np.zeros((ncomp, nth))
+    best = np.zeros(ncomp)
+    st = EstimateStats()
+    rc = H.emub_estimate_thetas_multi_devices(dev.ctypes.data_as(_ip), len(dev), _P(X), d, n, d, _P(Z), ncomp, ncomp, kernel, order,
+                                              max_slots, ctypes.byref(o), _P(th), _P(best), ctypes.byref(st))
     if rc not in (OK, EDOM):
         _check(rc)
     return th, best, dict(rc=rc, evaluations=st.evaluations, batches=st.batches, success_count=st.success_count,

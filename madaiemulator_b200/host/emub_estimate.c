@@ -18,6 +18,8 @@ void emub_estimate_default_opts(emub_estimate_opts *o)
 	o->tol = 0.5;
 	o->eps_abs = 0.1;
 	o->step_max = 30;
+	o->first_component = 0;
+	o->component_stride = 1;
 }
 
 /* modelstruct.c:188-213 */
@@ -257,7 +259,7 @@ static int estimate_impl(emub_model *model, int ncomp, const double *ranges, con
 		chain_t *c = &fr.chains[i];
 		c->fr = &fr; c->id = i; c->best_lhood = SCREWUPVALUE;
 		c->comp = i / per_comp; c->first_try = i % per_comp; c->try_stride = per_comp;
-		c->seed = o.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)c->comp;
+		c->seed = o.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(o.first_component + c->comp * (o.component_stride > 0 ? o.component_stride : 1));
 		c->x = (double *)calloc(1, vb); c->g = (double *)calloc(1, vb);
 		c->cx = (double *)calloc(1, vb); c->cg = (double *)calloc(1, vb);
 		c->best_thetas = (double *)calloc(1, vb);
@@ -336,4 +338,80 @@ static int estimate_impl(emub_model *model, int ncomp, const double *ranges, con
 	pthread_mutex_destroy(&fr.mu); pthread_cond_destroy(&fr.cv_disp); pthread_cond_destroy(&fr.cv_done);
 	if (rc != EMUB_OK) return rc;
 	return nfailed_comp ? EMUB_EDOM : EMUB_OK;
+}
+
+/* ---- components sharded over devices ------------------------------------------------------------------ */
+typedef struct {
+	int device, g, ndev;
+	const double *X, *Z;
+	int ldx, n, d, ldz, ncomp, kernel, order, max_slots;
+	emub_estimate_opts opts;
+	double *thetas_out, *best;
+	emub_estimate_stats stats;
+	int rc;
+} dev_job;
+
+static void *dev_main(void *arg)
+{
+	dev_job *j = (dev_job *)arg;
+	int nloc = 0;
+	for (int c = j->g; c < j->ncomp; c += j->ndev) nloc++;
+	if (nloc == 0) { j->rc = EMUB_OK; return NULL; }
+	const int nth = (j->kernel == EMUB_POWEREXP) ? j->d + 2 : 3;
+	emub_ctx *ctx = NULL;
+	emub_model *m = NULL;
+	double *Y = (double *)malloc(sizeof(double) * (size_t)j->n * nloc);
+	for (int i = 0; i < j->n; i++)
+		for (int k = 0; k < nloc; k++) Y[(size_t)i * nloc + k] = j->Z[(size_t)i * j->ldz + j->g + k * j->ndev];
+	double *ranges = (double *)malloc(sizeof(double) * 2 * (size_t)nth);
+	double *th = (double *)calloc((size_t)nloc * nth, sizeof(double));
+	double *best = (double *)calloc((size_t)nloc, sizeof(double));
+	emub_optimization_ranges(j->kernel, j->X, j->ldx, j->n, j->d, ranges);
+	j->rc = emub_ctx_create(j->device, &ctx);
+	if (j->rc == EMUB_OK) j->rc = emub_model_create(ctx, j->X, j->ldx, j->n, j->d, Y, j->kernel, j->order, j->max_slots, &m);
+	if (j->rc == EMUB_OK) j->rc = emub_model_set_training_multi(m, Y, nloc, nloc);
+	if (j->rc == EMUB_OK) {
+		j->opts.first_component = j->g;
+		j->opts.component_stride = j->ndev;
+		j->rc = emub_estimate_thetas_multi(m, nloc, ranges, &j->opts, th, best, &j->stats);
+		for (int k = 0; k < nloc; k++) {
+			memcpy(j->thetas_out + (size_t)(j->g + k * j->ndev) * nth, th + (size_t)k * nth, sizeof(double) * (size_t)nth);
+			j->best[j->g + k * j->ndev] = best[k];
+		}
+	}
+	if (m) emub_model_destroy(m);
+	if (ctx) emub_ctx_destroy(ctx);
+	free(Y); free(ranges); free(th); free(best);
+	return NULL;
+}
+
+int emub_estimate_thetas_multi_devices(const int *devices, int ndev, const double *X, int ldx, int n, int d,
+                                       const double *Z, int ldz, int ncomp, int kernel, int regression_order,
+                                       int max_slots, const emub_estimate_opts *opts_in, double *thetas_out,
+                                       double *best_lhood, emub_estimate_stats *stats)
+{
+	if (!devices || ndev < 1 || ndev > 64 || !X || !Z || ncomp < 1 || !thetas_out || !best_lhood) return EMUB_EINVAL;
+	dev_job jobs[64];
+	pthread_t th[64];
+	emub_estimate_opts o;
+	if (opts_in) o = *opts_in; else emub_estimate_default_opts(&o);
+	for (int g = 0; g < ndev; g++) {
+		dev_job *j = &jobs[g];
+		memset(j, 0, sizeof(*j));
+		j->device = devices[g]; j->g = g; j->ndev = ndev; j->X = X; j->Z = Z; j->ldx = ldx; j->n = n; j->d = d; j->ldz = ldz;
+		j->ncomp = ncomp; j->kernel = kernel; j->order = regression_order; j->max_slots = max_slots; j->opts = o;
+		j->thetas_out = thetas_out; j->best = best_lhood;
+		pthread_create(&th[g], NULL, dev_main, j);
+	}
+	int rc = EMUB_OK;
+	if (stats) memset(stats, 0, sizeof(*stats));
+	for (int g = 0; g < ndev; g++) {
+		pthread_join(th[g], NULL);
+		if (jobs[g].rc != EMUB_OK && rc == EMUB_OK) rc = jobs[g].rc;
+		if (stats) {
+			stats->evaluations += jobs[g].stats.evaluations; stats->batches += jobs[g].stats.batches;
+			stats->success_count += jobs[g].stats.success_count; stats->finite_count += jobs[g].stats.finite_count;
+		}
+	}
+	return rc;
 }

@@ -26,6 +26,9 @@ typedef struct {
 	double tol;               /* 0.5   maxmultimin.c:645 */
 	double eps_abs;           /* 0.1   maxmultimin.c:650 */
 	int step_max;             /* 30    maxmultimin.c:641 */
+	/* start-point stream of local component k: seed + (first_component + k * component_stride) * 0x9E3779B97F4A7C15,
+	 * so that components keep their streams when they are sharded over devices (defaults 0 and 1) */
+	int first_component, component_stride;
 } emub_estimate_opts;
 
 typedef struct {
@@ -69,6 +72,17 @@ int emub_estimate_thetas_from(emub_model *model, const double *ranges, const dou
  */
 int emub_estimate_thetas_multi(emub_model *model, int ncomp, const double *ranges, const emub_estimate_opts *opts,
                                double *thetas_out, double *best_lhood, emub_estimate_stats *stats);
+
+/*
+ * The same over several GPUs of one box: PCA components are independent scalar GPs on a shared design,
+ * component c goes to device devices[c % ndev]; one host thread, context and model per device, no exchange
+ * between devices, the thetas are gathered on the host.  Z is the n x ncomp training matrix (row stride ldz).
+ * Results are identical to a single-device emub_estimate_thetas_multi with the same seed.
+ */
+int emub_estimate_thetas_multi_devices(const int *devices, int ndev, const double *X, int ldx, int n, int d,
+                                       const double *Z, int ldz, int ncomp, int kernel, int regression_order,
+                                       int max_slots, const emub_estimate_opts *opts, double *thetas_out,
+                                       double *best_lhood, emub_estimate_stats *stats);
 
 #ifdef __cplusplus
 }

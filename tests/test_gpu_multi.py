@@ -111,3 +111,21 @@ def test_multi_simple_fixture_shape():
     X, Y = ds.load_input_model_file(MULTI_SIMPLE)
     assert X.shape == (100, 3) and Y.shape == (100, 6)
     assert ds.pca_decompose(Y, 0.99)["nr"] <= 5
+
+
+def test_components_shard_over_two_gpus(ctx):
+    """cfg4 pattern: PCA components sharded over the GPUs of one box, thetas gathered on the host -- identical to
+    the single-device run (same per-component start-point streams)."""
+    import torch
+    from madaiemulator_b200 import engine
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    X, Y, pca = _multi_problem(n=100)
+    Z, nr = pca["Z"], pca["nr"]
+    m = engine.Model(ctx, X, Z[:, 0], 1, 0, max_slots=32)
+    m.set_training_multi(Z)
+    th1, best1, _ = engine.estimate_thetas_multi(m, nr, max_tries=6, nchains=6, seed=3)
+    m.close()
+    th2, best2, st = engine.estimate_thetas_multi_devices([0, 1], X, Z, 1, 0, max_tries=6, nchains=6, seed=3, max_slots=32)
+    assert st["rc"] == 0
+    assert np.array_equal(th1, th2) and np.array_equal(best1, best2)
