@@ -85,7 +85,7 @@ int emub_loglik_grad_batch(emub_model *m, const double *thetas, int B, int want_
  * fronts of all components of a multivariate model (estimate_multi, multivar_support.c:20-27) share one batch */
 int emub_loglik_grad_batch_comp(emub_model *m, const double *thetas, const int *comp, int B, int want_grad,
                                 double *negL, double *grad, double *sigma2, int *status);
-/* same, but thetas / outputs are DEVICE pointers (out: B x (nthetas+2) doubles per point:
+/* same, but thetas / outputs are DEVICE pointers (out: B x (nthetas+3) doubles per point:
  * negL, sigma2, status, logdet, grad[nthetas-1]); asynchronous on the context's streams until
  * emub_ctx_synchronize. */
 int emub_loglik_grad_batch_dev(emub_model *m, const double *d_thetas, int B, int want_grad, double *d_out);

@@ -259,6 +259,7 @@ static void build_schedules(emub_model *m, std::vector<GemmTask> &tasks)
 }
 
 static void free_query_ws(emub_model *m);
+extern "C" void emub_model_destroy(emub_model *m);
 static int regression_fns(int order, int d) { if (order < 0 || order > 3) order = 0; return 1 + order * d; }
 
 extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n, int d, const double *y, int kernel,
@@ -271,7 +272,7 @@ extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n,
 	const int p = regression_fns(order, d);
 	if (p + 1 > MAXNCP) return set_err(EMUB_EINVAL, "emub_model_create: 1 + order*d + 1 must be <= 48%s");
 	CUDA_TRY(cudaSetDevice(ctx->device));
-	emub_model *m = new emub_model();
+	emub_model *m = new emub_model();  // value-initialised: every pointer starts out null, so a failed set-up can be torn down
 	m->ctx = ctx; m->n = n; m->d = d; m->p = p; m->kernel = kernel; m->order = order;
 	m->ncp = ((p + 1) + 7) / 8 * 8;
 	m->nth = (kernel == EMUB_POWEREXP) ? d + 2 : 3;
@@ -280,57 +281,67 @@ extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n,
 	m->mat = (size_t)m->npad * m->npad;
 	m->last_count = 0;
 	size_t free_b = 0, total_b = 0;
-	CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+	if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { delete m; return set_err(EMUB_ECUDA, "emub_model_create: cudaMemGetInfo failed%s"); }
 	const size_t per_slot = 3 * m->mat * sizeof(double) + (size_t)m->npad * m->ncp * 16 + (1 << 20);
 	int slots = (int)std::min<size_t>(64, (size_t)(0.6 * (double)free_b) / per_slot);
 	if (max_slots > 0) slots = std::min(slots, max_slots);
 	if (slots < 1) { delete m; return set_err(EMUB_ENOMEM, "emub_model_create: not enough device memory for one slot%s"); }
+#define MODEL_TRY(expr)                                                                                                  \
+	do {                                                                                                                 \
+		cudaError_t e__ = (expr);                                                                                        \
+		if (e__ != cudaSuccess) {                                                                                        \
+			emub_model_destroy(m);                                                                                       \
+			return set_err(e__ == cudaErrorMemoryAllocation ? EMUB_ENOMEM : EMUB_ECUDA, "CUDA: %s (emub_model_create:%d)", \
+			               cudaGetErrorString(e__), __LINE__);                                                           \
+		}                                                                                                                \
+	} while (0)
 	m->nslots = slots;
 
 	std::vector<double> Xp((size_t)m->npad * d, 0.0);
 	for (int i = 0; i < n; i++) memcpy(&Xp[(size_t)i * d], X + (size_t)i * ldx, sizeof(double) * d);
-	CUDA_TRY(cudaMalloc(&m->dX, Xp.size() * sizeof(double)));
-	CUDA_TRY(cudaMemcpy(m->dX, Xp.data(), Xp.size() * sizeof(double), cudaMemcpyHostToDevice));
-	CUDA_TRY(cudaMalloc(&m->dy, sizeof(double) * n));
-	CUDA_TRY(cudaMemcpy(m->dy, y, sizeof(double) * n, cudaMemcpyHostToDevice));
-	CUDA_TRY(cudaMalloc(&m->dYh, sizeof(double) * (size_t)m->npad * m->ncp));
+	MODEL_TRY(cudaMalloc(&m->dX, Xp.size() * sizeof(double)));
+	MODEL_TRY(cudaMemcpy(m->dX, Xp.data(), Xp.size() * sizeof(double), cudaMemcpyHostToDevice));
+	MODEL_TRY(cudaMalloc(&m->dy, sizeof(double) * n));
+	MODEL_TRY(cudaMemcpy(m->dy, y, sizeof(double) * n, cudaMemcpyHostToDevice));
+	MODEL_TRY(cudaMalloc(&m->dYh, sizeof(double) * (size_t)m->npad * m->ncp));
 	m->ncomp = 1;
 	m->qws = nullptr;
 	std::vector<GemmTask> tasks;
 	build_schedules(m, tasks);
 	if (tasks.empty()) tasks.push_back({0, 0, 0, 0, 0});
-	CUDA_TRY(cudaMalloc(&m->dTasks, tasks.size() * sizeof(GemmTask)));
-	CUDA_TRY(cudaMemcpy(m->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
+	MODEL_TRY(cudaMalloc(&m->dTasks, tasks.size() * sizeof(GemmTask)));
+	MODEL_TRY(cudaMemcpy(m->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
 	const size_t S = slots;
-	CUDA_TRY(cudaMalloc(&m->bufA, S * m->mat * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->bufW, S * m->mat * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->bufT, S * m->mat * sizeof(double)));
-	CUDA_TRY(cudaMemset(m->bufW, 0, S * m->mat * sizeof(double)));
-	CUDA_TRY(cudaMemset(m->bufT, 0, S * m->mat * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->dUG, S * m->npad * m->ncp * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->dAB, S * m->npad * m->ncp * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->dConsts, S * CONST_STRIDE * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->dLogdet, S * m->nblk * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->dGramPart, S * m->nblk * MAXNCP * MAXNCP * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->dRes, S * RES_STRIDE * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->bufA, S * m->mat * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->bufW, S * m->mat * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->bufT, S * m->mat * sizeof(double)));
+	MODEL_TRY(cudaMemset(m->bufW, 0, S * m->mat * sizeof(double)));
+	MODEL_TRY(cudaMemset(m->bufT, 0, S * m->mat * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dUG, S * m->npad * m->ncp * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dAB, S * m->npad * m->ncp * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dConsts, S * CONST_STRIDE * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dLogdet, S * m->nblk * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dGramPart, S * m->nblk * MAXNCP * MAXNCP * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dRes, S * RES_STRIDE * sizeof(double)));
 	const size_t nt64 = m->npad / CT, ntl = nt64 * (nt64 + 1) / 2;
-	CUDA_TRY(cudaMalloc(&m->dGradPart, S * ntl * MAXD * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->dMinv, S * MAXNCP * MAXNCP * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->dThetas, S * (MAXD + 2) * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->dOut, S * (MAXD + 6) * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&m->dInfo, S * sizeof(int)));
-	CUDA_TRY(cudaMalloc(&m->dComp, S * sizeof(int)));
-	CUDA_TRY(cudaMemset(m->dComp, 0, S * sizeof(int)));
-	CUDA_TRY(cudaMallocHost(&m->hComp, S * sizeof(int)));
-	CUDA_TRY(cudaMallocHost(&m->hThetas, S * (MAXD + 2) * sizeof(double)));
-	CUDA_TRY(cudaMallocHost(&m->hRes, S * RES_STRIDE * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dGradPart, S * ntl * MAXD * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dMinv, S * MAXNCP * MAXNCP * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dThetas, S * (MAXD + 2) * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dOut, S * (MAXD + 6) * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dInfo, S * sizeof(int)));
+	MODEL_TRY(cudaMalloc(&m->dComp, S * sizeof(int)));
+	MODEL_TRY(cudaMemset(m->dComp, 0, S * sizeof(int)));
+	MODEL_TRY(cudaMallocHost(&m->hComp, S * sizeof(int)));
+	MODEL_TRY(cudaMallocHost(&m->hThetas, S * (MAXD + 2) * sizeof(double)));
+	MODEL_TRY(cudaMallocHost(&m->hRes, S * RES_STRIDE * sizeof(double)));
 	cudaStream_t st = ctx->streams[0];
 	{
 		LaunchScope ls(ctx, EMUB_K_SMALL, 0, st);
 		k_build_yh<<<(m->npad + 127) / 128, 128, 0, st>>>(m->dX, m->dy, 1, n, m->npad, d, order, m->ncp, m->dYh);
 	}
-	CUDA_TRY(cudaStreamSynchronize(st));
-	CUDA_TRY(cudaGetLastError());
+	MODEL_TRY(cudaStreamSynchronize(st));
+	MODEL_TRY(cudaGetLastError());
+#undef MODEL_TRY
 	*out = m;
 	return EMUB_OK;
 }
@@ -776,6 +787,7 @@ extern "C" int emub_debug_cholesky(emub_model *m, const double *theta_less_amp, 
 }
 
 // ---- prediction ------------------------------------------------------------------------------------------
+extern "C" void emub_emulator_destroy(emub_emulator *e);
 static int ensure_query_ws(emub_model *m)
 {
 	if (m->qws) return EMUB_OK;
@@ -839,11 +851,12 @@ extern "C" int emub_emulator_create_comp(emub_model *m, int comp, const double *
 	e->kappa = hc[0] + hc[1];  // c(x*, x*) = amp + nugget   (emulator_struct.c:135)
 	for (int i = 0; i < m->p; i++) e->hbeta[i] = m->hRes[RES_BETA + i];
 	const size_t sUG = (size_t)m->npad * m->ncp;
-	CUDA_TRY(cudaMalloc(&e->W, m->mat * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&e->AB, sUG * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&e->beta, MAXNCP * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&e->Minv, MAXNCP * MAXNCP * sizeof(double)));
-	CUDA_TRY(cudaMalloc(&e->consts, CONST_STRIDE * sizeof(double)));
+	if (cudaMalloc(&e->W, m->mat * sizeof(double)) != cudaSuccess || cudaMalloc(&e->AB, sUG * sizeof(double)) != cudaSuccess ||
+	    cudaMalloc(&e->beta, MAXNCP * sizeof(double)) != cudaSuccess || cudaMalloc(&e->Minv, MAXNCP * MAXNCP * sizeof(double)) != cudaSuccess ||
+	    cudaMalloc(&e->consts, CONST_STRIDE * sizeof(double)) != cudaSuccess) {
+		emub_emulator_destroy(e);
+		return set_err(EMUB_ENOMEM, "emub_emulator_create: out of device memory%s");
+	}
 	CUDA_TRY(cudaMemcpyAsync(e->W, m->bufW, m->mat * sizeof(double), cudaMemcpyDeviceToDevice, st));
 	CUDA_TRY(cudaMemcpyAsync(e->AB, m->dAB, sUG * sizeof(double), cudaMemcpyDeviceToDevice, st));
 	CUDA_TRY(cudaMemcpyAsync(e->beta, m->dRes + RES_BETA, MAXNCP * sizeof(double), cudaMemcpyDeviceToDevice, st));

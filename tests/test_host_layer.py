@@ -70,3 +70,21 @@ def test_estimate_thetas_reaches_reference_likelihood(name, tries):
         assert ours3 >= ref_scored - 1e-6 * max(1.0, abs(ref_scored)), (ours3, ref_scored)
     m.close()
     ctx.close()
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU only: the reference's own evalFnGradMulti from oracle/_ref) prints one JSON
+    line with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, check=True, timeout=600).stdout.decode().strip().split("\n")[-1]
+    d = json.loads(out)
+    assert d["impl"] == "reference" and d["metric"] == "loglik_grad_evals_per_s" and d["unit"] == "evals/s"
+    assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["n"] == 4096 and d["config"]["d"] == 10
