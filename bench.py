@@ -25,6 +25,10 @@ if ROOT not in sys.path:
 
 N_MODEL, D_MODEL, ORDER = 4096, 10, 0
 CPU_SAMPLE_N = 768
+# dram__bytes_read.sum + dram__bytes_write.sum over the 125 k_gemm launches of ONE likelihood+gradient batch of 8
+# matrices at n=4096 (ncu, profiles/r01_gemm_family_traffic.txt); the matrices of a batch are independent, so the
+# traffic of a batch of B is B/8 of this
+GEMM_FAMILY_DRAM_BYTES_B8, GEMM_FAMILY_LAUNCHES = 5.348e9, 125
 
 
 def parse_args():
@@ -322,7 +326,10 @@ def main():
                        "share": round(v["ms"] / tot_ms, 4)} for k, v in prof.items() if v["launches"]}
         roofline = {"bound": "tensor", "kernel": "emub::k_gemm (FP64 DMMA tile engine: Cholesky TRSM/SYRK, inverse merge, W^T W)",
                     "achieved": round(achieved, 3), "peak": round(peak, 3), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                    "traffic": None,
+                    "traffic": GEMM_FAMILY_DRAM_BYTES_B8 * (B / 8.0) / GEMM_FAMILY_LAUNCHES if N_MODEL == 4096 else None,
+                    "traffic_source": "ncu dram bytes summed over the 125 k_gemm launches of one batch of 8 (profiles/"
+                                      "r01_gemm_family_traffic.txt), scaled by B/8, per launch on average; 669 MB per evaluation "
+                                      "for ~10 passes over 67 MB lower-triangular matrices",
                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
                                    "DMMA issue-rate microbenchmark 37.1 TFLOP/s, profiles/r01_dmma_probe.txt)",
                     "launches": g_n, "avg_launch_ms": round(g_ms / max(1, g_n), 4),
