@@ -24,7 +24,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_MODEL, D_MODEL, ORDER = 4096, 10, 0
-CPU_SAMPLE_N = 768
+CPU_SAMPLE_N = 1024
 # dram__bytes_read.sum + dram__bytes_write.sum over the 125 k_gemm launches of ONE likelihood+gradient batch of 8
 # matrices at n=4096 (ncu, profiles/r01_gemm_family_traffic.txt); the matrices of a batch are independent, so the
 # traffic of a batch of B is B/8 of this
@@ -114,7 +114,7 @@ class ClockSampler:
 
 def cpu_reference_rate(nthreads, reps=1):
     """The reference's own evalFnGradMulti (oracle/_ref, compiled from the reference sources; falls back to the
-    plain-C port) on a bounded sample: n=768 (one evaluation is ~5 s on one core), one independent evaluation per
+    plain-C port) on a bounded sample: n=1024 (one evaluation is ~13 s on one core), one independent evaluation per
     thread -- the reference's own parallel model (estimate_threaded.c:97,172) -- extrapolated to n=4096 by the
     cubic cost of the path ((2(T-1)+1) n^3 flops)."""
     from madaiemulator_b200 import datasets as ds
