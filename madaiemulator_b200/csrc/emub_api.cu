@@ -97,7 +97,7 @@ struct emub_model {
 	int lauum_off, lauum_cnt;
 	double lauum_flops;
 	double *bufA, *bufW, *bufT;
-	double *dUG, *dAB, *dConsts, *dLogdet, *dGramPart, *dRes, *dGradPart, *dMinv, *dThetas, *dOut;
+	double *dUG, *dAB, *dConsts, *dLogdet, *dGramPart, *dRes, *dGradPart, *dMinv, *dThetas;
 	int *dInfo;
 	double *hThetas, *hRes;  // pinned
 	int last_count;
@@ -327,7 +327,6 @@ extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n,
 	MODEL_TRY(cudaMalloc(&m->dGradPart, S * ntl * MAXD * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dMinv, S * MAXNCP * MAXNCP * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dThetas, S * (MAXD + 2) * sizeof(double)));
-	MODEL_TRY(cudaMalloc(&m->dOut, S * (MAXD + 6) * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dInfo, S * sizeof(int)));
 	MODEL_TRY(cudaMalloc(&m->dComp, S * sizeof(int)));
 	MODEL_TRY(cudaMemset(m->dComp, 0, S * sizeof(int)));
@@ -354,7 +353,7 @@ extern "C" void emub_model_destroy(emub_model *m)
 	cudaFree(m->dX); cudaFree(m->dy); cudaFree(m->dYh); cudaFree(m->dTasks);
 	cudaFree(m->bufA); cudaFree(m->bufW); cudaFree(m->bufT);
 	cudaFree(m->dUG); cudaFree(m->dAB); cudaFree(m->dConsts); cudaFree(m->dLogdet); cudaFree(m->dGramPart);
-	cudaFree(m->dRes); cudaFree(m->dGradPart); cudaFree(m->dMinv); cudaFree(m->dThetas); cudaFree(m->dOut); cudaFree(m->dInfo);
+	cudaFree(m->dRes); cudaFree(m->dGradPart); cudaFree(m->dMinv); cudaFree(m->dThetas); cudaFree(m->dInfo);
 	cudaFree(m->dComp);
 	cudaFreeHost(m->hThetas); cudaFreeHost(m->hRes); cudaFreeHost(m->hComp);
 	free_query_ws(m);
@@ -981,7 +980,6 @@ extern "C" int emub_predict_multi(emub_emulator *const *emus, int nr, const doub
 		memcpy(proj.data() + nt + (size_t)nt * nr, evals, sizeof(double) * nr);
 		CUDA_TRY(cudaMemcpy(w->dProj, proj.data(), sizeof(double) * proj.size(), cudaMemcpyHostToDevice));
 	}
-	const int nout = nt > 0 ? nt : nr;
 	for (int done = 0; done < mq; done += w->mqc) {
 		const int cnt = std::min(w->mqc, mq - done);
 		for (int q = 0; q < cnt; q++) memcpy(w->hQ + (size_t)q * m->d, pts + (size_t)(done + q) * ldp, sizeof(double) * m->d);
@@ -1011,7 +1009,6 @@ extern "C" int emub_predict_multi(emub_emulator *const *emus, int nr, const doub
 					var[(size_t)(done + q) * nr + j] = w->hOut[(size_t)NTMAX * w->mqc + (size_t)j * cnt + q];
 				}
 		}
-		(void)nout;
 	}
 	CUDA_TRY(cudaGetLastError());
 	return EMUB_OK;

@@ -183,11 +183,6 @@ __global__ void k_build_yh(const double *__restrict__ X, const double *__restric
 	if (order >= 2) for (int k = 0; k < d; k++) row[2 + d + k] = x[k] * x[k];
 	if (order >= 3) for (int k = 0; k < d; k++) row[2 + 2 * d + k] = x[k] * x[k] * x[k];
 }
-__global__ void k_set_y(const double *__restrict__ y, int n, int ncp, double *__restrict__ Yh)
-{
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) Yh[(size_t)i * ncp] = y[i];
-}
 
 // ---- POTF2: Cholesky of one 128 x 128 diagonal block + its triangular inverse, register resident ----
 // The block is cut into a 16 x 16 grid of 8 x 8 sub-blocks; the 136 lower ones live in the registers of
