@@ -57,3 +57,27 @@ def test_reference_restart_driver_on_the_engine(oracles):
     best_dro, th_dro = dro.max_with_multimin(6, 5)
     assert abs(best_dro - best_ref) < 1e-6 * max(1.0, abs(best_ref))
     assert np.max(np.abs(th_dro - th_ref)) < 1e-4
+
+
+def test_emuplusplus_front_end_on_the_engine():
+    """The reference's C++ wrapper (src/EmuPlusPlus.cpp) and its example driver (test/emuplusplus-test/src/example.cpp),
+    both unmodified, linked against the drop-in library: same printed means / errors as on the CPU reference build."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_bin = os.path.join(root, "oracle", "_ref", "emuplusplus_ref")
+    dro_bin = os.path.join(root, "oracle", "_ref", "emuplusplus_dropin")
+    if not (os.path.exists(ref_bin) and os.path.exists(dro_bin)):
+        pytest.skip("oracle/_ref EmuPlusPlus builds not present")
+    snap = os.path.join(root, "tests", "golden", "cli", "multi-simple-o0.snapshot")
+    pts = "".join(open(os.path.join(root, "tests", "golden", "cli", "multi-simple.points")).readlines()[:25]).encode()
+    a = subprocess.run([ref_bin, snap], input=pts, capture_output=True, check=True, timeout=300).stdout.decode().split("\n")
+    b = subprocess.run([dro_bin, snap], input=pts, capture_output=True, check=True, timeout=300).stdout.decode().split("\n")
+    assert len(a) == len(b) and len(a) > 70
+    for la, lb in zip(a, b):
+        if la.startswith("# mean:") or la.startswith("# err:"):
+            va = np.array(la.split(":")[1].split(), dtype=np.float64)
+            vb = np.array(lb.split(":")[1].split(), dtype=np.float64)
+            assert np.allclose(va, vb, rtol=2e-6, atol=1e-9)  # cout prints 6 significant digits
+        else:
+            assert la == lb
