@@ -192,6 +192,12 @@ __global__ void k_build_yh(const double *__restrict__ X, const double *__restric
 // The same row operations are applied to the identity, stored in the slots of the already eliminated
 // columns, so when the sweep ends the registers hold L^-1; finished columns of L go to a packed shared
 // array and are written out coalesced.
+// Measured (tools/potf2_bench.cu + ncu source view): ~1500 cycles per column = 104 us per block; 35 % of the warp
+// time is spent at the barrier waiting for the warp that holds the pivot / column / row owners, i.e. the sweep is
+// bound by the latency of ~300 dependent instructions per column, not by its 64 DFMA per thread.  Variants that
+// hoist the role tests, let only the pivot owner take the rsqrt or move the L output to a helper warp measure the
+// same (102-112 us).  It is 2 % of a step at B = 64; the next step is a dedicated panel warp (shuffle-based
+// 8-column panels, rank-8 register updates).
 // grid (B), POTF2_THREADS threads, dynamic smem POTF2_SMEM_BYTES.
 constexpr int POTF2_THREADS = 160;
 constexpr int POTF2_NBLOCKS = 136;

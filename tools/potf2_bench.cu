@@ -7,7 +7,7 @@
 #include "../madaiemulator_b200/csrc/emub_kernels.cuh"
 using namespace emub;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
-int main()
+int main(int argc, char **argv)
 {
 	const int n = 128, B = 8;
 	std::vector<double> A((size_t)B * n * n);
@@ -19,11 +19,19 @@ int main()
 			}
 	double *dA, *dL, *dW, *dlog; int *dinfo;
 	size_t bytes = A.size() * 8;
-	CK(cudaMalloc(&dA, bytes)); CK(cudaMalloc(&dL, bytes)); CK(cudaMalloc(&dW, bytes)); CK(cudaMalloc(&dlog, B * 8)); CK(cudaMalloc(&dinfo, B * 4));
+	CK(cudaMalloc(&dA, bytes)); CK(cudaMalloc(&dL, bytes)); CK(cudaMalloc(&dW, bytes)); CK(cudaMalloc(&dlog, (B + 128) * 8)); CK(cudaMalloc(&dinfo, B * 4));
 	CK(cudaMemcpy(dA, A.data(), bytes, cudaMemcpyHostToDevice));
 	CK(cudaMemset(dinfo, 0, B * 4));
 	CK(cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
 	cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+	if (argc > 1) {  // profiling mode: 148 CTAs on the same block (stride 0), one launch
+		k_potf2<<<148, POTF2_THREADS, POTF2_SMEM_BYTES>>>(dA, 0, dL, 0, dW, 0, n, 0, 1, dlog, dinfo);
+		CK(cudaDeviceSynchronize());
+		k_potf2<<<148, POTF2_THREADS, POTF2_SMEM_BYTES>>>(dA, 0, dL, 0, dW, 0, n, 0, 1, dlog, dinfo);
+		CK(cudaDeviceSynchronize());
+		printf("profiled launch done\n");
+		return 0;
+	}
 	for (int nb : {1, 8}) {
 		for (int w = 0; w < 3; w++) k_potf2<<<nb, POTF2_THREADS, POTF2_SMEM_BYTES>>>(dA, n * n, dL, n * n, dW, n * n, n, 0, 1, dlog, dinfo);
 		CK(cudaDeviceSynchronize());
