@@ -44,6 +44,9 @@ const char *emub_version(void);
 void *emub_ctx_stream(emub_ctx *ctx);
 /* number of concurrently scheduled matrix groups (streams); 1..4, default 2 */
 int emub_ctx_set_groups(emub_ctx *ctx, int ngroups);
+/* the launch sequence of a batch chunk (~160 dependent kernels per group) is captured once into a CUDA graph and
+ * replayed; on by default (EMUB_NO_GRAPHS=1 or on = 0 issues the kernels one by one) */
+int emub_ctx_use_graphs(emub_ctx *ctx, int on);
 
 /* ---- model ------------------------------------------------------------------------------------ */
 /* replaces alloc_modelstruct_2 (modelstruct.c:282) + makeHMatrix_fnptr (regression.c:100):

@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "../../include/emu_b200.h"
@@ -50,6 +51,7 @@ struct ProfAcc { double ms; long long launches; double work; };
 struct emub_ctx {
 	int device;
 	int ngroups;
+	int use_graphs;  // replay captured CUDA graphs for the per-chunk launch sequences (default on; EMUB_NO_GRAPHS=1 disables)
 	cudaStream_t streams[4];
 	int profile;
 	ProfAcc prof[EMUB_K_NFAMILIES];
@@ -101,6 +103,8 @@ struct emub_model {
 	int *dInfo;
 	double *hThetas, *hRes;  // pinned
 	int last_count;
+	std::vector<std::pair<unsigned long long, cudaGraphExec_t>> graphs;   // captured chunk sequences, by configuration
+	std::vector<std::pair<unsigned long long, long long>> graph_launches;  // kernels per replay (for emub_launch_count)
 };
 
 // query workspace: one chunk of up to mqc points
@@ -139,6 +143,7 @@ extern "C" int emub_ctx_create(int device, emub_ctx **out)
 	memset(c, 0, sizeof(*c));
 	c->device = device;
 	c->ngroups = 2;
+	c->use_graphs = getenv("EMUB_NO_GRAPHS") ? 0 : 1;
 	for (int g = 0; g < 4; g++) {
 		CUDA_TRY(cudaStreamCreateWithFlags(&c->streams[g], cudaStreamNonBlocking));
 		CUDA_TRY(cudaEventCreateWithFlags(&c->gev[g], cudaEventDisableTiming));
@@ -171,6 +176,12 @@ extern "C" int emub_ctx_set_groups(emub_ctx *c, int ng)
 {
 	if (!c || ng < 1 || ng > 4) return set_err(EMUB_EINVAL, "emub_ctx_set_groups: 1..4%s");
 	c->ngroups = ng;
+	return EMUB_OK;
+}
+extern "C" int emub_ctx_use_graphs(emub_ctx *c, int on)
+{
+	if (!c) return EMUB_EINVAL;
+	c->use_graphs = on ? 1 : 0;
 	return EMUB_OK;
 }
 extern "C" int emub_ctx_synchronize(emub_ctx *c)
@@ -356,6 +367,7 @@ extern "C" void emub_model_destroy(emub_model *m)
 	cudaFree(m->dRes); cudaFree(m->dGradPart); cudaFree(m->dMinv); cudaFree(m->dThetas); cudaFree(m->dInfo);
 	cudaFree(m->dComp);
 	cudaFreeHost(m->hThetas); cudaFreeHost(m->hRes); cudaFreeHost(m->hComp);
+	for (auto &g : m->graphs) cudaGraphExecDestroy(g.second);
 	free_query_ws(m);
 	delete m;
 }
@@ -383,6 +395,10 @@ extern "C" int emub_model_set_training_multi(emub_model *m, const double *Y, int
 	double *dY = nullptr;
 	CUDA_TRY(cudaMalloc(&dY, sizeof(double) * (size_t)m->n * ncomp));
 	CUDA_TRY(cudaMemcpy2D(dY, sizeof(double) * ncomp, Y, sizeof(double) * ldy, sizeof(double) * ncomp, m->n, cudaMemcpyHostToDevice));
+	// captured graphs hold the address of dYh: drop them whenever the training data is rebuilt
+	for (auto &g : m->graphs) cudaGraphExecDestroy(g.second);
+	m->graphs.clear();
+	m->graph_launches.clear();
 	if (ncomp != m->ncomp) {
 		cudaFree(m->dYh);
 		CUDA_TRY(cudaMalloc(&m->dYh, sizeof(double) * (size_t)ncomp * m->npad * m->ncp));
@@ -572,11 +588,10 @@ static void run_group(emub_model *m, cudaStream_t st, int s0, int count, int nth
 }
 
 // split `count` slots over the context's stream groups and run them concurrently
-static int run_chunk(emub_model *m, int count, int nth_in, int mode, int want_grad, int emulator_mode)
+// the launch sequence of one chunk: fork stream 0 to the other groups, run them, join back
+static int issue_chunk(emub_model *m, int count, int nth_in, int mode, int want_grad, int emulator_mode, int ng)
 {
 	emub_ctx *c = m->ctx;
-	int ng = c->profile ? 1 : std::min(c->ngroups, count);
-	// stream 0 is the entry/exit stream: fork to the other groups, join back
 	CUDA_TRY(cudaEventRecord(c->gev[0], c->streams[0]));
 	int s0 = 0;
 	for (int g = 0; g < ng; g++) {
@@ -589,8 +604,50 @@ static int run_chunk(emub_model *m, int count, int nth_in, int mode, int want_gr
 			CUDA_TRY(cudaStreamWaitEvent(c->streams[0], c->gev[g], 0));
 		}
 	}
-	CUDA_TRY(cudaGetLastError());
+	return EMUB_OK;
+}
+
+// One chunk = a fixed sequence of ~160 dependent launches per stream group whose arguments (device buffers,
+// sizes) depend only on (count, theta layout, gradient / emulator flags, groups): it is captured ONCE into a CUDA
+// graph (the fork/join events between the group streams become graph edges) and replayed afterwards, so the
+// host pays one launch per chunk and the small dependent kernels of the recursion run back to back.
+static int run_chunk(emub_model *m, int count, int nth_in, int mode, int want_grad, int emulator_mode)
+{
+	emub_ctx *c = m->ctx;
+	const int ng = c->profile ? 1 : std::min(c->ngroups, count);
 	m->last_count = count;
+	if (c->profile || !c->use_graphs) {
+		int rc = issue_chunk(m, count, nth_in, mode, want_grad, emulator_mode, ng);
+		if (rc) return rc;
+		CUDA_TRY(cudaGetLastError());
+		return EMUB_OK;
+	}
+	const unsigned long long key = ((unsigned long long)count << 32) | ((unsigned)nth_in << 16) | ((unsigned)ng << 8) |
+	                               ((unsigned)mode << 2) | ((unsigned)(want_grad != 0) << 1) | (unsigned)(emulator_mode != 0);
+	cudaGraphExec_t exec = nullptr;
+	for (auto &g : m->graphs)
+		if (g.first == key) { exec = g.second; break; }
+	if (!exec) {
+		const long long launches_before = c->launches;
+		cudaGraph_t graph = nullptr;
+		CUDA_TRY(cudaStreamBeginCapture(c->streams[0], cudaStreamCaptureModeThreadLocal));
+		int rc = issue_chunk(m, count, nth_in, mode, want_grad, emulator_mode, ng);
+		cudaError_t ce = cudaStreamEndCapture(c->streams[0], &graph);
+		if (rc != EMUB_OK || ce != cudaSuccess || !graph) {
+			if (graph) cudaGraphDestroy(graph);
+			cudaGetLastError();
+			return rc != EMUB_OK ? rc : set_err(EMUB_ECUDA, "CUDA graph capture failed: %s", cudaGetErrorString(ce));
+		}
+		ce = cudaGraphInstantiate(&exec, graph, 0);
+		cudaGraphDestroy(graph);
+		if (ce != cudaSuccess) return set_err(EMUB_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+		m->graphs.push_back({key, exec});
+		m->graph_launches.push_back({key, c->launches - launches_before});
+		c->launches = launches_before;  // counted per replay below
+	}
+	for (auto &g : m->graph_launches)
+		if (g.first == key) { c->launches += g.second; break; }
+	CUDA_TRY(cudaGraphLaunch(exec, c->streams[0]));
 	return EMUB_OK;
 }
 

@@ -28,7 +28,7 @@ FAMILIES = ["cov", "potf2", "gemm_chol", "gemm_trtri", "gemm_lauum", "skinny", "
 # every symbol include/emu_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [
     "emub_ctx_create", "emub_ctx_destroy", "emub_last_error", "emub_version", "emub_ctx_stream",
-    "emub_ctx_set_groups", "emub_model_create", "emub_model_destroy", "emub_model_nthetas",
+    "emub_ctx_set_groups", "emub_ctx_use_graphs", "emub_model_create", "emub_model_destroy", "emub_model_nthetas",
     "emub_model_nregression_fns", "emub_model_slots", "emub_model_set_training", "emub_model_set_training_multi",
     "emub_model_ncomponents", "emub_loglik_grad_batch_comp", "emub_emulator_create_comp", "emub_predict_multi", "emub_cov_matrix",
     "emub_h_matrix", "emub_k_vectors", "emub_loglik_grad_batch", "emub_loglik_grad_batch_dev",
@@ -67,6 +67,7 @@ def lib():
     L.emub_ctx_stream.argtypes = [_vp]
     L.emub_ctx_stream.restype = _vp
     L.emub_ctx_set_groups.argtypes = [_vp, _ci]
+    L.emub_ctx_use_graphs.argtypes = [_vp, _ci]
     L.emub_ctx_synchronize.argtypes = [_vp]
     L.emub_model_create.argtypes = [_vp, _dp, _ci, _ci, _ci, _dp, _ci, _ci, _ci, ctypes.POINTER(_vp)]
     L.emub_model_destroy.argtypes = [_vp]
@@ -131,6 +132,9 @@ class Context:
 
     def set_groups(self, g):
         _check(self.L.emub_ctx_set_groups(self.h, g))
+
+    def use_graphs(self, on):
+        _check(self.L.emub_ctx_use_graphs(self.h, 1 if on else 0))
 
     def stream(self):
         return self.L.emub_ctx_stream(self.h)
