@@ -68,3 +68,7 @@ for k, v in pr.items():
     if v["launches"]:
         rate = v["work"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0
         print("%-12s %6d launches %9.3f ms  work/time = %8.3f T/s" % (k, v["launches"], v["ms"], rate))
+import time as _t
+t0 = _t.time(); e2 = m.emulator(full); t1 = _t.time()
+print("emulator set-up (covariance + factor + inverse + regression) at n=4096: %.1f ms" % ((t1 - t0) * 1e3))
+e2.close()
