@@ -81,3 +81,56 @@ def test_emuplusplus_front_end_on_the_engine():
             assert np.allclose(va, vb, rtol=2e-6, atol=1e-9)  # cout prints 6 significant digits
         else:
             assert la == lb
+
+
+def test_reference_cli_trains_on_the_engine(tmp_path):
+    """BASELINE configs 0/1 end to end through the reference's UNCHANGED CLI: `interactive_emulator estimate_thetas`
+    (input reader, PCA, model structs and snapshot writer are the reference's; estimate_thetas_threaded is the glue
+    -> batched GPU restarts).  north_star: the likelihood reached must be no worse than the reference's own training
+    (tests/golden/cli/*.snapshot were trained by the reference CLI on the CPU with 8 x 50 restarts)."""
+    import ctypes
+    import os
+    import subprocess
+    from madaiemulator_b200 import engine
+    from oracle.pyoracle import PortOracle
+    from tests.test_interactive_stream import _Snap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "oracle", "_ref", "interactive_emulator_dropin")
+    if not os.path.exists(cli):
+        pytest.skip("oracle/_ref/interactive_emulator_dropin not built")
+    H = engine.host_lib()
+    H.emub_snapshot_load_path.restype = ctypes.POINTER(_Snap)
+    H.emub_snapshot_load_path.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+
+    def thetas_of(path):
+        err = ctypes.create_string_buffer(256)
+        sp = H.emub_snapshot_load_path(path.encode(), err, 256)
+        assert sp, err.value
+        s = sp.contents
+        out = []
+        for c in range(s.nr):
+            comp = s.components[c]
+            n, d = comp.nmodel_points, comp.nparams
+            out.append((np.ctypeslib.as_array(comp.xmodel, (n * d,)).reshape(n, d).copy(),
+                        np.ctypeslib.as_array(comp.training_vector, (n,)).copy(),
+                        np.ctypeslib.as_array(comp.thetas, (comp.nthetas,)).copy(), comp.regression_order))
+        return out
+
+    # the reference's input file, reconstructed from its own snapshot (X and the training matrix are stored verbatim)
+    ref_snap = os.path.join(root, "tests", "golden", "cli", "uni-simple-o1.snapshot")
+    tok = open(ref_snap).read().split()
+    nt, nr, d, n = int(tok[0]), int(tok[1]), int(tok[2]), int(tok[3])
+    inp = tmp_path / "input_model_file.dat"
+    inp.write_text("%d\n%d\n%d\n" % (nt, d, n) + "\n".join(tok[6:6 + n * d]) + "\n" + "\n".join(tok[6 + n * d:6 + n * d + n * nt]) + "\n")
+    out_snap = tmp_path / "trained_on_gpu.snapshot"
+    env = dict(os.environ, EMUB_TRIES="400", EMUB_SLOTS="64", EMUB_SEED="5")  # the reference run: 8 threads x 50 restarts
+    subprocess.run([cli, "estimate_thetas", str(inp), str(out_snap), "--regression_order=1"], check=True, timeout=600, env=env,
+                   stdout=subprocess.DEVNULL)
+    ours, ref = thetas_of(str(out_snap)), thetas_of(ref_snap)
+    assert len(ours) == len(ref) == 1
+    for (X1, y1, th1, o1), (X0, y0, th0, o0) in zip(ours, ref):
+        assert np.allclose(X1, X0) and np.allclose(y1, y0, atol=1e-12) and o1 == o0 == 1
+        po = PortOracle(X0, y0, 1, o0)
+        l_ours = -po.loglik_grad(th1[1:], want_grad=False)["negL"]
+        l_ref = -po.loglik_grad(th0[1:], want_grad=False)["negL"]
+        assert l_ours >= l_ref - 1e-3 * max(1.0, abs(l_ref)), (l_ours, l_ref)
