@@ -8,6 +8,7 @@
 #include <math.h>
 #include "emub_gemm.cuh"
 #include "emub_exp.cuh"
+#include "emub_potf2.cuh"
 
 namespace emub {
 
@@ -182,165 +183,6 @@ __global__ void k_build_yh(const double *__restrict__ X, const double *__restric
 	if (order >= 1) for (int k = 0; k < d; k++) row[2 + k] = x[k];
 	if (order >= 2) for (int k = 0; k < d; k++) row[2 + d + k] = x[k] * x[k];
 	if (order >= 3) for (int k = 0; k < d; k++) row[2 + 2 * d + k] = x[k] * x[k] * x[k];
-}
-
-// ---- POTF2: Cholesky of one 128 x 128 diagonal block + its triangular inverse, register resident ----
-// The block is cut into a 16 x 16 grid of 8 x 8 sub-blocks; the 136 lower ones live in the registers of
-// 136 threads (64 doubles each).  Right-looking column sweep with ONE barrier per column: the owners of
-// column j / row j publish their raw values to a double-buffered shared array, everybody derives the
-// pivot 1/a_jj itself and applies the rank-1 update  a(i,c) -= a(i,j) a(c,j) / a_jj  from registers.
-// The same row operations are applied to the identity, stored in the slots of the already eliminated
-// columns, so when the sweep ends the registers hold L^-1; finished columns of L go to a packed shared
-// array and are written out coalesced.
-// Measured (tools/potf2_bench.cu + ncu source view): ~1500 cycles per column = 104 us per block; 35 % of the warp
-// time is spent at the barrier waiting for the warp that holds the pivot / column / row owners, i.e. the sweep is
-// bound by the latency of ~300 dependent instructions per column, not by its 64 DFMA per thread.  Variants that
-// hoist the role tests, let only the pivot owner take the rsqrt or move the L output to a helper warp measure the
-// same (102-112 us).  It is 2 % of a step at B = 64; the next step is a dedicated panel warp (shuffle-based
-// 8-column panels, rank-8 register updates).
-// grid (B), POTF2_THREADS threads, dynamic smem POTF2_SMEM_BYTES.
-constexpr int POTF2_THREADS = 160;
-constexpr int POTF2_NBLOCKS = 136;
-constexpr int POTF2_LPACK = TB * (TB + 1) / 2;
-constexpr int POTF2_SMEM_BYTES = (POTF2_LPACK + 5 * TB) * 8;
-
-__global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, long long strideA, double *Lbase, long long strideL,
-                                                         double *Wbase, long long strideW, int ld, int kblk, int nblk,
-                                                         double *__restrict__ logdet_parts, int *__restrict__ info)
-{
-	extern __shared__ double sm[];
-	double *Lp = sm;                    // packed lower triangle of L: (i, c) at i (i + 1) / 2 + c
-	double *colbuf = sm + POTF2_LPACK;  // [2][128]
-	double *rowbuf = colbuf + 2 * TB;   // [2][128]
-	const int tid = threadIdx.x, b = blockIdx.x;
-	const size_t blk = (size_t)kblk * TB * ld + (size_t)kblk * TB;
-	const double *A = Abase + b * strideA + blk;
-	double *Lg = Lbase + b * strideL + blk;
-	double *Wg = Wbase + b * strideW + blk;
-	const bool active = tid < POTF2_NBLOCKS;
-	int bi = 0, bj = 0;
-	if (active) {
-		while ((bi + 1) * (bi + 2) / 2 <= tid) bi++;
-		bj = tid - bi * (bi + 1) / 2;
-	}
-	double a[8][8];
-	if (active) {
-#pragma unroll
-		for (int r = 0; r < 8; r++) {
-			const double *src = A + (size_t)(bi * 8 + r) * ld + bj * 8;
-#pragma unroll
-			for (int c = 0; c < 8; c += 2) {
-				double2 v = *reinterpret_cast<const double2 *>(src + c);
-				a[r][c] = v.x;
-				a[r][c + 1] = v.y;
-			}
-		}
-	}
-	// strictly upper sub-blocks of both outputs are zero
-	for (int idx = tid; idx < TB * TB; idx += POTF2_THREADS) {
-		const int i = idx >> 7, c = idx & 127;
-		if ((c >> 3) > (i >> 3)) {
-			Lg[(size_t)i * ld + c] = 0.0;
-			Wg[(size_t)i * ld + c] = 0.0;
-		}
-	}
-	int bad = 0;
-	double *pivots = rowbuf + 2 * TB;  // [128] a_jj at elimination time, for the log-determinant
-	for (int jb = 0; jb < 16; jb++) {
-		// jj is unrolled so that every register-array index below is a compile-time constant
-#pragma unroll
-		for (int jj = 0; jj < 8; jj++) {
-			const int j = jb * 8 + jj;
-			double *cb = colbuf + (j & 1) * TB;
-			double *rb = rowbuf + (j & 1) * TB;
-			if (active) {
-				if (bj == jb) {
-#pragma unroll
-					for (int r = 0; r < 8; r++) cb[bi * 8 + r] = a[r][jj];
-				}
-				if (bi == jb) {
-#pragma unroll
-					for (int c = 0; c < 8; c++) rb[bj * 8 + c] = a[jj][c];
-				}
-			}
-			__syncthreads();
-			const double p = cb[j];
-			const bool ok = (p > 0.0) && (p < 1.0e300);
-			if (!ok) bad = 1;
-			const double pp = ok ? p : 1.0;
-			const double isq = rsqrt(pp);
-			const double sq = pp * isq;
-			const double ip = isq * isq;
-			if (tid == 0) pivots[j] = pp;
-			if (active && bi >= jb) {
-				double l[8], v[8];
-#pragma unroll
-				for (int r = 0; r < 8; r++) {
-					const int gi = bi * 8 + r;
-					const double raw = cb[gi];
-					l[r] = (gi > j) ? raw : 0.0;
-					if (bj == jb && gi >= j) Lp[gi * (gi + 1) / 2 + j] = (gi == j) ? sq : raw * isq;
-				}
-#pragma unroll
-				for (int c = 0; c < 8; c++) {
-					const int gc = bj * 8 + c;
-					const double src = (gc < j) ? rb[gc] : cb[gc];
-					v[c] = (gc == j) ? ip : src * ip;
-				}
-				if (bj == jb) {
-					// the slot of column j now starts to hold the inverse: -L(i,j) / L(j,j) = 0 - a(i,j) / a(j,j)
-#pragma unroll
-					for (int r = 0; r < 8; r++)
-						if (bi * 8 + r > j) a[r][jj] = 0.0;
-				}
-				if (bi == jb) {
-					// row j of the inverse becomes final
-#pragma unroll
-					for (int c = 0; c < 8; c++) {
-						const int gc = bj * 8 + c;
-						if (gc < j) a[jj][c] *= isq;
-						else if (gc == j) a[jj][c] = isq;
-					}
-				}
-#pragma unroll
-				for (int r = 0; r < 8; r++)
-#pragma unroll
-					for (int c = 0; c < 8; c++) a[r][c] -= l[r] * v[c];
-			}
-		}
-	}
-	__syncthreads();
-	double logsum = 0.0;
-	if (tid < 32) {
-		// sum_j log L_jj = 0.5 sum_j log a_jj, fixed order
-		double s = log(pivots[tid]) + log(pivots[tid + 32]) + log(pivots[tid + 64]) + log(pivots[tid + 96]);
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-		logsum = 0.5 * s;
-	}
-	__syncthreads();
-	if (tid == 0) {
-		logdet_parts[(size_t)b * nblk + kblk] = logsum;
-		if (bad) info[b] = 1;
-	}
-	if (active) {
-#pragma unroll
-		for (int r = 0; r < 8; r++) {
-			const int gi = bi * 8 + r;
-			double *dst = Wg + (size_t)gi * ld + bj * 8;
-#pragma unroll
-			for (int c = 0; c < 8; c += 2) {
-				double2 v;
-				v.x = (bj * 8 + c <= gi) ? a[r][c] : 0.0;
-				v.y = (bj * 8 + c + 1 <= gi) ? a[r][c + 1] : 0.0;
-				*reinterpret_cast<double2 *>(dst + c) = v;
-			}
-		}
-	}
-	for (int idx = tid; idx < TB * TB; idx += POTF2_THREADS) {
-		const int i = idx >> 7, c = idx & 127;
-		if ((c >> 3) <= (i >> 3)) Lg[(size_t)i * ld + c] = (c <= i) ? Lp[i * (i + 1) / 2 + c] : 0.0;
-	}
 }
 
 // ---- skinny products ---------------------------------------------------------------------------------
