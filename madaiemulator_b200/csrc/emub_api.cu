@@ -115,6 +115,10 @@ struct QueryWs {
 	double *dOutM, *dOutV, *dProj;                // back-projected outputs (mqc x ntmax), projection data
 	GemmTask *dTasks;
 	double *hQ, *hOut;  // pinned
+	// second set for the double-buffered chunk walk (walk_query_chunks): [0] aliases dQ / hQ / hOut
+	double *dQb[2], *hQb[2], *hOutb[2];
+	cudaStream_t copy_stream;
+	cudaEvent_t evIn[2], evOut[2];
 };
 constexpr int NTMAX = 64;  // observables per multivariate model supported by the fused back-projection
 
@@ -382,6 +386,9 @@ static void free_query_ws(emub_model *m)
 	cudaFree(w->dQ); cudaFree(w->dK); cudaFree(w->dVsq); cudaFree(w->dKA); cudaFree(w->dMean); cudaFree(w->dVar);
 	cudaFree(w->dOutM); cudaFree(w->dOutV); cudaFree(w->dProj); cudaFree(w->dTasks);
 	cudaFreeHost(w->hQ); cudaFreeHost(w->hOut);
+	cudaFree(w->dQb[1]); cudaFreeHost(w->hQb[1]); cudaFreeHost(w->hOutb[1]);
+	if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
+	for (int i = 0; i < 2; i++) { if (w->evIn[i]) cudaEventDestroy(w->evIn[i]); if (w->evOut[i]) cudaEventDestroy(w->evOut[i]); }
 	delete w;
 	m->qws = nullptr;
 }
@@ -866,6 +873,15 @@ static int ensure_query_ws(emub_model *m)
 	CUDA_TRY(cudaMalloc(&w->dProj, sizeof(double) * (size_t)(NTMAX + NTMAX * NTMAX + NTMAX)));
 	CUDA_TRY(cudaMallocHost(&w->hQ, sizeof(double) * (size_t)mqc * m->d));
 	CUDA_TRY(cudaMallocHost(&w->hOut, sizeof(double) * 2 * (size_t)std::max(NTMAX, 1) * mqc));
+	CUDA_TRY(cudaMalloc(&w->dQb[1], sizeof(double) * (size_t)mqc * m->d));
+	CUDA_TRY(cudaMallocHost(&w->hQb[1], sizeof(double) * (size_t)mqc * m->d));
+	CUDA_TRY(cudaMallocHost(&w->hOutb[1], sizeof(double) * 2 * (size_t)std::max(NTMAX, 1) * mqc));
+	w->dQb[0] = w->dQ; w->hQb[0] = w->hQ; w->hOutb[0] = w->hOut;
+	CUDA_TRY(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) {
+		CUDA_TRY(cudaEventCreateWithFlags(&w->evIn[i], cudaEventDisableTiming));
+		CUDA_TRY(cudaEventCreateWithFlags(&w->evOut[i], cudaEventDisableTiming));
+	}
 	// V = W K, one task per row block (longest K first); the batch dimension walks the query blocks
 	std::vector<GemmTask> tasks;
 	for (int i = m->nblk - 1; i >= 0; i--) tasks.push_back({(long long)i * TB * m->npad, 0, 0, (i + 1) * TB, i | TASK_TRIM_END_SR0});
@@ -987,6 +1003,49 @@ extern "C" int emub_predict_batch_dev(emub_emulator *e, const double *d_pts, int
 	return EMUB_OK;
 }
 
+// Chunked, double-buffered walk over mq query points: packing + host-to-device copy of chunk i+1 (copy stream) and the
+// copy-out of chunk i-1 (host) overlap the kernels of chunk i.  compute(cnt, dQ, hOut) enqueues the chunk's kernels and
+// its device-to-host copies on streams[0]; collect(done, cnt, hOut) moves a finished chunk into the caller's arrays.
+template <class Compute, class Collect>
+static int walk_query_chunks(emub_model *m, const double *pts, int ldp, int mq, Compute compute, Collect collect)
+{
+	QueryWs *w = m->qws;
+	cudaStream_t st = m->ctx->streams[0], cp = w->copy_stream;
+	const int nchunks = (mq + w->mqc - 1) / w->mqc;
+	auto stage = [&](int i) -> int {
+		const int b = i & 1, done = i * w->mqc, cnt = std::min(w->mqc, mq - done);
+		if (i >= 2) {
+			CUDA_TRY(cudaEventSynchronize(w->evIn[b]));          // hQb[b] has left the host
+			CUDA_TRY(cudaStreamWaitEvent(cp, w->evOut[b], 0));   // chunk i-2 no longer reads dQb[b]
+		}
+		if (ldp == m->d) memcpy(w->hQb[b], pts + (size_t)done * ldp, sizeof(double) * (size_t)cnt * m->d);
+		else for (int q = 0; q < cnt; q++) memcpy(w->hQb[b] + (size_t)q * m->d, pts + (size_t)(done + q) * ldp, sizeof(double) * m->d);
+		CUDA_TRY(cudaMemcpyAsync(w->dQb[b], w->hQb[b], sizeof(double) * (size_t)cnt * m->d, cudaMemcpyHostToDevice, cp));
+		CUDA_TRY(cudaEventRecord(w->evIn[b], cp));
+		return EMUB_OK;
+	};
+	if (nchunks > 0) { int rc = stage(0); if (rc) return rc; }
+	for (int i = 0; i < nchunks; i++) {
+		const int b = i & 1, cnt = std::min(w->mqc, mq - i * w->mqc);
+		CUDA_TRY(cudaStreamWaitEvent(st, w->evIn[b], 0));
+		int rc = compute(cnt, w->dQb[b], w->hOutb[b]);
+		if (rc) { cudaStreamSynchronize(st); cudaStreamSynchronize(cp); return rc; }
+		CUDA_TRY(cudaEventRecord(w->evOut[b], st));
+		if (i + 1 < nchunks) { rc = stage(i + 1); if (rc) return rc; }
+		if (i > 0) {
+			CUDA_TRY(cudaEventSynchronize(w->evOut[b ^ 1]));
+			collect((i - 1) * w->mqc, w->mqc, w->hOutb[b ^ 1]);
+		}
+	}
+	if (nchunks > 0) {
+		const int i = nchunks - 1;
+		CUDA_TRY(cudaEventSynchronize(w->evOut[i & 1]));
+		collect(i * w->mqc, mq - i * w->mqc, w->hOutb[i & 1]);
+	}
+	CUDA_TRY(cudaGetLastError());
+	return EMUB_OK;
+}
+
 extern "C" int emub_predict_batch(emub_emulator *e, const double *pts, int ldp, int mq, double *mean, double *var)
 {
 	if (!e || !pts || !mean || !var || mq < 0 || ldp < e->m->d) return set_err(EMUB_EINVAL, "emub_predict_batch: bad argument%s");
@@ -995,19 +1054,19 @@ extern "C" int emub_predict_batch(emub_emulator *e, const double *pts, int ldp, 
 	{ int rc0 = ensure_query_ws(m); if (rc0) return rc0; }
 	QueryWs *w = m->qws;
 	cudaStream_t st = m->ctx->streams[0];
-	for (int done = 0; done < mq; done += w->mqc) {
-		const int cnt = std::min(w->mqc, mq - done);
-		for (int q = 0; q < cnt; q++) memcpy(w->hQ + (size_t)q * m->d, pts + (size_t)(done + q) * ldp, sizeof(double) * m->d);
-		CUDA_TRY(cudaMemcpyAsync(w->dQ, w->hQ, sizeof(double) * (size_t)cnt * m->d, cudaMemcpyHostToDevice, st));
-		int rc = predict_chunk(e, st, w->dQ, cnt, w->dMean, w->dVar);
-		if (rc) return rc;
-		CUDA_TRY(cudaMemcpyAsync(w->hOut, w->dMean, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
-		CUDA_TRY(cudaMemcpyAsync(w->hOut + w->mqc, w->dVar, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
-		CUDA_TRY(cudaStreamSynchronize(st));
-		memcpy(mean + done, w->hOut, sizeof(double) * cnt);
-		memcpy(var + done, w->hOut + w->mqc, sizeof(double) * cnt);
-	}
-	return EMUB_OK;
+	return walk_query_chunks(
+	    m, pts, ldp, mq,
+	    [&](int cnt, const double *dQ, double *hOut) -> int {
+		    int rc = predict_chunk(e, st, dQ, cnt, w->dMean, w->dVar);
+		    if (rc) return rc;
+		    CUDA_TRY(cudaMemcpyAsync(hOut, w->dMean, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+		    CUDA_TRY(cudaMemcpyAsync(hOut + w->mqc, w->dVar, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+		    return EMUB_OK;
+	    },
+	    [&](int done, int cnt, const double *hOut) {
+		    memcpy(mean + done, hOut, sizeof(double) * cnt);
+		    memcpy(var + done, hOut + w->mqc, sizeof(double) * cnt);
+	    });
 }
 
 // emulate_point_multi (multivar_support.c:103-157) for mq points: every PCA component's (mean, var) for the whole
@@ -1037,36 +1096,38 @@ extern "C" int emub_predict_multi(emub_emulator *const *emus, int nr, const doub
 		memcpy(proj.data() + nt + (size_t)nt * nr, evals, sizeof(double) * nr);
 		CUDA_TRY(cudaMemcpy(w->dProj, proj.data(), sizeof(double) * proj.size(), cudaMemcpyHostToDevice));
 	}
-	for (int done = 0; done < mq; done += w->mqc) {
-		const int cnt = std::min(w->mqc, mq - done);
-		for (int q = 0; q < cnt; q++) memcpy(w->hQ + (size_t)q * m->d, pts + (size_t)(done + q) * ldp, sizeof(double) * m->d);
-		CUDA_TRY(cudaMemcpyAsync(w->dQ, w->hQ, sizeof(double) * (size_t)cnt * m->d, cudaMemcpyHostToDevice, st));
-		for (int j = 0; j < nr; j++) {
-			int rc = predict_chunk(emus[j], st, w->dQ, cnt, w->dMean + (size_t)j * w->mqc, w->dVar + (size_t)j * w->mqc);
-			if (rc) return rc;
-		}
-		if (nt > 0) {
-			{
-				LaunchScope ls(m->ctx, EMUB_K_PRED_FINAL, 0, st);
-				k_backproject<<<(cnt + 127) / 128, 128, 0, st>>>(w->dMean, w->dVar, w->mqc, cnt, nt, nr, w->dProj, w->dProj + nt,
-				                                                 w->dProj + nt + (size_t)nt * nr, w->dOutM, w->dOutV);
-			}
-			CUDA_TRY(cudaMemcpyAsync(w->hOut, w->dOutM, sizeof(double) * (size_t)cnt * nt, cudaMemcpyDeviceToHost, st));
-			CUDA_TRY(cudaMemcpyAsync(w->hOut + (size_t)NTMAX * w->mqc, w->dOutV, sizeof(double) * (size_t)cnt * nt, cudaMemcpyDeviceToHost, st));
-			CUDA_TRY(cudaStreamSynchronize(st));
-			memcpy(mean + (size_t)done * nt, w->hOut, sizeof(double) * (size_t)cnt * nt);
-			memcpy(var + (size_t)done * nt, w->hOut + (size_t)NTMAX * w->mqc, sizeof(double) * (size_t)cnt * nt);
-		} else {
-			CUDA_TRY(cudaMemcpy2DAsync(w->hOut, sizeof(double) * cnt, w->dMean, sizeof(double) * w->mqc, sizeof(double) * cnt, nr, cudaMemcpyDeviceToHost, st));
-			CUDA_TRY(cudaMemcpy2DAsync(w->hOut + (size_t)NTMAX * w->mqc, sizeof(double) * cnt, w->dVar, sizeof(double) * w->mqc, sizeof(double) * cnt, nr, cudaMemcpyDeviceToHost, st));
-			CUDA_TRY(cudaStreamSynchronize(st));
-			for (int q = 0; q < cnt; q++)
-				for (int j = 0; j < nr; j++) {
-					mean[(size_t)(done + q) * nr + j] = w->hOut[(size_t)j * cnt + q];
-					var[(size_t)(done + q) * nr + j] = w->hOut[(size_t)NTMAX * w->mqc + (size_t)j * cnt + q];
-				}
-		}
-	}
-	CUDA_TRY(cudaGetLastError());
-	return EMUB_OK;
+	const size_t vofs = (size_t)NTMAX * w->mqc;  // variances start here in a host output buffer
+	return walk_query_chunks(
+	    m, pts, ldp, mq,
+	    [&](int cnt, const double *dQ, double *hOut) -> int {
+		    for (int j = 0; j < nr; j++) {
+			    int rc = predict_chunk(emus[j], st, dQ, cnt, w->dMean + (size_t)j * w->mqc, w->dVar + (size_t)j * w->mqc);
+			    if (rc) return rc;
+		    }
+		    if (nt > 0) {
+			    {
+				    LaunchScope ls(m->ctx, EMUB_K_PRED_FINAL, 0, st);
+				    k_backproject<<<(cnt + 127) / 128, 128, 0, st>>>(w->dMean, w->dVar, w->mqc, cnt, nt, nr, w->dProj, w->dProj + nt,
+				                                                     w->dProj + nt + (size_t)nt * nr, w->dOutM, w->dOutV);
+			    }
+			    CUDA_TRY(cudaMemcpyAsync(hOut, w->dOutM, sizeof(double) * (size_t)cnt * nt, cudaMemcpyDeviceToHost, st));
+			    CUDA_TRY(cudaMemcpyAsync(hOut + vofs, w->dOutV, sizeof(double) * (size_t)cnt * nt, cudaMemcpyDeviceToHost, st));
+		    } else {
+			    CUDA_TRY(cudaMemcpy2DAsync(hOut, sizeof(double) * cnt, w->dMean, sizeof(double) * w->mqc, sizeof(double) * cnt, nr, cudaMemcpyDeviceToHost, st));
+			    CUDA_TRY(cudaMemcpy2DAsync(hOut + vofs, sizeof(double) * cnt, w->dVar, sizeof(double) * w->mqc, sizeof(double) * cnt, nr, cudaMemcpyDeviceToHost, st));
+		    }
+		    return EMUB_OK;
+	    },
+	    [&](int done, int cnt, const double *hOut) {
+		    if (nt > 0) {
+			    memcpy(mean + (size_t)done * nt, hOut, sizeof(double) * (size_t)cnt * nt);
+			    memcpy(var + (size_t)done * nt, hOut + vofs, sizeof(double) * (size_t)cnt * nt);
+		    } else {
+			    for (int q = 0; q < cnt; q++)
+				    for (int j = 0; j < nr; j++) {
+					    mean[(size_t)(done + q) * nr + j] = hOut[(size_t)j * cnt + q];
+					    var[(size_t)(done + q) * nr + j] = hOut[vofs + (size_t)j * cnt + q];
+				    }
+		    }
+	    });
 }
