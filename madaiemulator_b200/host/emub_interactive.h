@@ -31,7 +31,16 @@ int emub_multi_emulator_nparams(const emub_multi_emulator *me);
 /* emulate_point_multi / _pca for a block: mean, var are m x nt (pca_output: first nr of each row are meaningful) */
 int emub_multi_emulator_predict(emub_multi_emulator *me, const double *pts, int m, int pca_output, double *mean, double *var);
 
-/* the interactive_mode loop.  block_points <= 0 selects 16384.  Returns EMUB_OK at end of input; *npoints (optional)
+/* Text -> doubles, the input side of the stream: buf[0, len) must end on a separator (blank, newline, tab, CR, comma)
+ * or be the end of the input, and buf[len] must be writable.  Converts up to max values with strtod (the same
+ * conversion as the reference's fscanf("%lf")), tokens counted and converted on `threads` host threads when the text
+ * is long.  Returns the number of values; *consumed = bytes used up (the rest belongs to the next block); *bad = 1
+ * when a token that is not a number ended the conversion. */
+size_t emub_parse_doubles(char *buf, size_t len, double *out, size_t max, int threads, size_t *consumed, int *bad);
+
+/* the interactive_mode loop: reader / device / writer stages on their own host threads over a ring of blocks, text
+ * conversion and "%.17f" formatting spread over EMUB_IO_THREADS (default: online cores - 2) worker threads.
+ * block_points <= 0 selects 65536 per device.  Returns EMUB_OK at end of input; *npoints (optional)
  * = points answered.  binary != 0 selects the BINARY_INTERACTIVE_MODE framing (raw doubles in and out, :119). */
 int emub_interactive_stream(emub_multi_emulator *me, FILE *in, FILE *out, int quiet, int pca_output, int binary,
                             int block_points, long long *npoints);

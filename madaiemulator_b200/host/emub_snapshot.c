@@ -103,6 +103,94 @@ emub_snapshot *emub_snapshot_load_path(const char *path, char *err, int errlen)
 	return s;
 }
 
+/* "%.17lf " per value, one row per line: the exact bytes of dump_multi_modelstruct / dump_modelstruct_2 */
+static void put_rows(FILE *f, const double *a, size_t rows, size_t cols)
+{
+	for (size_t i = 0; i < rows; i++) {
+		for (size_t j = 0; j < cols; j++) fprintf(f, "%.17lf ", a[i * cols + j]);
+		fprintf(f, "\n");
+	}
+}
+
+int emub_snapshot_save(const emub_snapshot *s, FILE *f)
+{
+	if (!s || !f) return -1;
+	const size_t n = (size_t)s->nmodel_points, d = (size_t)s->nparams, nt = (size_t)s->nt, nr = (size_t)s->nr;
+	/* multi_modelstruct.c:358-401 */
+	fprintf(f, "%d\n%d\n%d\n%d\n%d\n%d\n", s->nt, s->nr, s->nparams, s->nmodel_points, s->cov_fn_index, s->regression_order);
+	put_rows(f, s->xmodel, n, d);
+	put_rows(f, s->training_matrix, n, nt);
+	put_rows(f, s->pca_evals_r, 1, nr);
+	put_rows(f, s->pca_evecs_r, nt, nr);
+	put_rows(f, s->pca_zmatrix, n, nr);
+	for (size_t c = 0; c < nr; c++) { /* modelstruct.c:381-408 */
+		const emub_snapshot_component *m = &s->components[c];
+		fprintf(f, "%d\n%d\n%d\n%d\n%d\n%d\n%d\n%.17lf\n%d\n%d\n", m->nthetas, m->nparams, m->nmodel_points, m->nemulate_points,
+		        m->regression_order, m->nregression_fns, m->fixed_nugget_mode, m->fixed_nugget, m->cov_fn_index, m->use_data_scales);
+		for (int i = 0; i < m->nthetas; i++) fprintf(f, "%.17lf %.17lf\n", m->grad_ranges[2 * i], m->grad_ranges[2 * i + 1]);
+		put_rows(f, m->xmodel, n, d);
+		put_rows(f, m->training_vector, 1, n);
+		put_rows(f, m->thetas, 1, (size_t)m->nthetas);
+		put_rows(f, m->sample_scales, 1, d);
+	}
+	return ferror(f) ? -1 : 0;
+}
+
+int emub_snapshot_save_path(const emub_snapshot *s, const char *path)
+{
+	FILE *f = fopen(path, "w");
+	if (!f) return -1;
+	int rc = emub_snapshot_save(s, f);
+	if (fclose(f) != 0) rc = -1;
+	return rc;
+}
+
+/* A snapshot for nr scalar GPs that share one design, from plain arrays (what estimate_multi + dump leave behind):
+ * Z is n x nr (component training vectors), thetas nr x nthetas.  With nt == nr, unit eigenvalues and identity
+ * eigenvectors the back-projection is the identity, i.e. the outputs are the components themselves. */
+emub_snapshot *emub_snapshot_from_arrays(const double *X, int n, int d, const double *Z, int nr, const double *thetas, int nthetas,
+                                         int cov_fn_index, int regression_order)
+{
+	if (!X || !Z || !thetas || n < 1 || d < 1 || nr < 1 || nthetas < 1) return NULL;
+	emub_snapshot *s = (emub_snapshot *)calloc(1, sizeof(*s));
+	s->nt = nr; s->nr = nr; s->nparams = d; s->nmodel_points = n; s->cov_fn_index = cov_fn_index; s->regression_order = regression_order;
+	const size_t N = (size_t)n, D = (size_t)d, R = (size_t)nr;
+	s->xmodel = (double *)malloc(sizeof(double) * N * D);
+	memcpy(s->xmodel, X, sizeof(double) * N * D);
+	/* training matrix = Z with its column means restored as zero: Y = Z, so ybar = column means of Z */
+	s->training_matrix = (double *)malloc(sizeof(double) * N * R);
+	memcpy(s->training_matrix, Z, sizeof(double) * N * R);
+	s->training_mean = (double *)calloc(R, sizeof(double));
+	for (size_t j = 0; j < R; j++) {
+		double sum = 0.0;
+		for (size_t i = 0; i < N; i++) sum += Z[i * R + j];
+		s->training_mean[j] = sum / (double)n;
+	}
+	s->pca_evals_r = (double *)malloc(sizeof(double) * R);
+	s->pca_evecs_r = (double *)calloc(R * R, sizeof(double));
+	s->pca_zmatrix = (double *)malloc(sizeof(double) * N * R);
+	for (size_t j = 0; j < R; j++) { s->pca_evals_r[j] = 1.0; s->pca_evecs_r[j * R + j] = 1.0; }
+	/* z = y - ybar so that ybar + 1 * z reproduces y */
+	for (size_t i = 0; i < N; i++)
+		for (size_t j = 0; j < R; j++) s->pca_zmatrix[i * R + j] = Z[i * R + j] - s->training_mean[j];
+	s->components = (emub_snapshot_component *)calloc(R, sizeof(emub_snapshot_component));
+	for (size_t c = 0; c < R; c++) {
+		emub_snapshot_component *m = &s->components[c];
+		m->nthetas = nthetas; m->nparams = d; m->nmodel_points = n; m->nemulate_points = 0;
+		m->regression_order = regression_order; m->nregression_fns = 1 + regression_order * d;
+		m->fixed_nugget_mode = 0; m->fixed_nugget = 0.0; m->cov_fn_index = cov_fn_index; m->use_data_scales = 1;
+		m->grad_ranges = (double *)calloc(2 * (size_t)nthetas, sizeof(double));
+		m->xmodel = (double *)malloc(sizeof(double) * N * D);
+		memcpy(m->xmodel, X, sizeof(double) * N * D);
+		m->training_vector = (double *)malloc(sizeof(double) * N);
+		for (size_t i = 0; i < N; i++) m->training_vector[i] = s->pca_zmatrix[i * R + c];
+		m->thetas = (double *)malloc(sizeof(double) * (size_t)nthetas);
+		memcpy(m->thetas, thetas + c * (size_t)nthetas, sizeof(double) * (size_t)nthetas);
+		m->sample_scales = (double *)calloc(D, sizeof(double));
+	}
+	return s;
+}
+
 void emub_snapshot_free(emub_snapshot *s)
 {
 	if (!s) return;

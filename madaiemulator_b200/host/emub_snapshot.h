@@ -36,6 +36,14 @@ typedef struct {
 /* returns NULL (and a message in err, if given) on a malformed file */
 emub_snapshot *emub_snapshot_load(FILE *f, char *err, int errlen);
 emub_snapshot *emub_snapshot_load_path(const char *path, char *err, int errlen);
+/* writer: the bytes dump_multi_modelstruct (multi_modelstruct.c:346-401) + dump_modelstruct_2 (modelstruct.c:375-409)
+ * produce for the same contents; 0 on success */
+int emub_snapshot_save(const emub_snapshot *s, FILE *f);
+int emub_snapshot_save_path(const emub_snapshot *s, const char *path);
+/* nr scalar GPs on one design as a snapshot with an identity back-projection (nt = nr, U = I, lambda = 1):
+ * Z n x nr, thetas nr x nthetas (full vectors, amplitude first) */
+emub_snapshot *emub_snapshot_from_arrays(const double *X, int n, int d, const double *Z, int nr, const double *thetas, int nthetas,
+                                         int cov_fn_index, int regression_order);
 void emub_snapshot_free(emub_snapshot *s);
 
 #ifdef __cplusplus

@@ -71,6 +71,120 @@ def test_snapshot_reader(name, nt, nr, d, n, order):
     assert b"malformed" in err.value
 
 
+@pytest.mark.parametrize("name", ["uni-simple-o1", "multi-simple-o0"])
+def test_snapshot_writer_is_byte_identical_to_the_reference_dump(name, tmp_path):
+    """load -> save reproduces the file the reference CLI wrote (dump_multi_modelstruct, multi_modelstruct.c:346-401)."""
+    from madaiemulator_b200 import engine
+    H = engine.host_lib()
+    H.emub_snapshot_load_path.restype = ctypes.POINTER(_Snap)
+    H.emub_snapshot_load_path.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    H.emub_snapshot_save_path.argtypes = [ctypes.POINTER(_Snap), ctypes.c_char_p]
+    H.emub_snapshot_free.argtypes = [ctypes.POINTER(_Snap)]
+    H.emub_snapshot_free.restype = None
+    path = os.path.join(CLI_DIR, name + ".snapshot")
+    err = ctypes.create_string_buffer(256)
+    sp = H.emub_snapshot_load_path(path.encode(), err, 256)
+    assert sp, err.value
+    out = str(tmp_path / "copy.snapshot")
+    assert H.emub_snapshot_save_path(sp, out.encode()) == 0
+    H.emub_snapshot_free(sp)
+    assert open(out, "rb").read() == open(path, "rb").read()
+
+
+def test_snapshot_from_arrays_round_trip(tmp_path):
+    from madaiemulator_b200 import engine
+    H = engine.host_lib()
+    H.emub_snapshot_from_arrays.restype = ctypes.POINTER(_Snap)
+    H.emub_snapshot_from_arrays.argtypes = [_dp, ctypes.c_int, ctypes.c_int, _dp, ctypes.c_int, _dp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    H.emub_snapshot_load_path.restype = ctypes.POINTER(_Snap)
+    H.emub_snapshot_load_path.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    H.emub_snapshot_save_path.argtypes = [ctypes.POINTER(_Snap), ctypes.c_char_p]
+    H.emub_snapshot_free.argtypes = [ctypes.POINTER(_Snap)]
+    H.emub_snapshot_free.restype = None
+    rng = np.random.default_rng(3)
+    n, d, nr = 40, 3, 2
+    X = np.ascontiguousarray(rng.uniform(-1, 1, (n, d)))
+    Z = np.ascontiguousarray(rng.normal(size=(n, nr)))
+    th = np.ascontiguousarray(rng.uniform(-3, 1, (nr, d + 2)))
+    sp = H.emub_snapshot_from_arrays(X.ctypes.data_as(_dp), n, d, Z.ctypes.data_as(_dp), nr, th.ctypes.data_as(_dp), d + 2, 1, 1)
+    assert sp
+    out = str(tmp_path / "made.snapshot")
+    assert H.emub_snapshot_save_path(sp, out.encode()) == 0
+    H.emub_snapshot_free(sp)
+    err = ctypes.create_string_buffer(256)
+    sp = H.emub_snapshot_load_path(out.encode(), err, 256)
+    assert sp, err.value
+    s = sp.contents
+    assert (s.nt, s.nr, s.nparams, s.nmodel_points, s.cov_fn_index, s.regression_order) == (nr, nr, d, n, 1, 1)
+    # "%.17lf" keeps 17 decimals, not 17 significant digits: values are reproduced to 1e-17 absolute
+    assert np.max(np.abs(np.ctypeslib.as_array(s.xmodel, (n * d,)) - X.ravel())) < 1e-16
+    mean = np.ctypeslib.as_array(s.training_mean, (nr,))
+    assert np.allclose(mean, Z.mean(axis=0), atol=1e-15)
+    for c in range(nr):
+        comp = s.components[c]
+        assert comp.nregression_fns == 1 + d and comp.nthetas == d + 2
+        assert np.max(np.abs(np.ctypeslib.as_array(comp.training_vector, (n,)) - (Z[:, c] - Z[:, c].mean()))) < 1e-15
+        assert np.max(np.abs(np.ctypeslib.as_array(comp.thetas, (d + 2,)) - th[c])) < 1e-16
+    # identity back-projection
+    assert np.array_equal(np.ctypeslib.as_array(s.pca_evecs_r, (nr * nr,)).reshape(nr, nr), np.eye(nr))
+    assert np.array_equal(np.ctypeslib.as_array(s.pca_evals_r, (nr,)), np.ones(nr))
+    H.emub_snapshot_free(sp)
+
+
+def _parse(H, text, maxvals, threads):
+    buf = ctypes.create_string_buffer(text, len(text) + 1)
+    out = np.full(maxvals + 4, -777.0)
+    consumed = ctypes.c_size_t(0)
+    bad = ctypes.c_int(0)
+    k = H.emub_parse_doubles(buf, len(text), out.ctypes.data_as(_dp), maxvals, threads, ctypes.byref(consumed), ctypes.byref(bad))
+    assert np.all(out[maxvals:] == -777.0)  # never writes past max
+    assert buf.raw[:len(text)] == text       # the text is left as it was
+    return out[:k], consumed.value, bad.value
+
+
+def test_parallel_text_parser():
+    """the input side of the stream: same values as strtod/float() token by token, whatever the thread count"""
+    from madaiemulator_b200 import engine
+    H = engine.host_lib()
+    H.emub_parse_doubles.restype = ctypes.c_size_t
+    H.emub_parse_doubles.argtypes = [ctypes.c_char_p, ctypes.c_size_t, _dp, ctypes.c_size_t, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_int)]
+    rng = np.random.default_rng(11)
+    vals = np.concatenate([rng.uniform(-3, 3, 30000), rng.normal(size=2000) * 1e-300, rng.normal(size=2000) * 1e300,
+                           [0.0, -0.0, 1e-320, 5e-324, 1.7976931348623157e308]])
+    rng.shuffle(vals)
+    seps = [" ", "\n", "\t", ", ", " \r\n", "  "]
+    fmts = ["%.17g", "%.17f", "%r", "%.3e", "%.10g"]
+    toks = []
+    for i, v in enumerate(vals):
+        f = fmts[i % len(fmts)]
+        toks.append(repr(float(v)) if f == "%r" else ((f % v) if abs(v) < 1e20 or "f" not in f else "%.17g" % v))
+    text = "".join(t + seps[i % len(seps)] for i, t in enumerate(toks)).encode()
+    assert len(text) > (1 << 16)  # long enough for the threaded path
+    expect = np.array([float(t) for t in toks])
+    for threads in (1, 3, 8):
+        got, consumed, bad = _parse(H, text, len(toks) + 10, threads)
+        assert bad == 0 and consumed == len(text)
+        assert np.array_equal(got.view(np.uint64), expect.view(np.uint64))  # bit-exact, signed zeros and denormals included
+        # a block that fills up in the middle: exactly max values, and the rest of the text parses to the remainder
+        for cap in (1, 777, len(toks) // 2, len(toks) - 1, len(toks)):
+            got, consumed, bad = _parse(H, text, cap, threads)
+            assert len(got) == cap and bad == 0
+            assert np.array_equal(got.view(np.uint64), expect[:cap].view(np.uint64))
+            rest, c2, _ = _parse(H, text[consumed:], len(toks), threads)
+            assert np.array_equal(rest.view(np.uint64), expect[cap:].view(np.uint64))
+    # a token that is not a number ends the conversion there (the reference's fscanf stops too)
+    broken = b"1.5 2.5\n3.5 oops 4.5\n" + text
+    for threads in (1, 8):
+        got, consumed, bad = _parse(H, broken, 100000, threads)
+        assert bad == 1 and list(got) == [1.5, 2.5, 3.5]
+    # short texts, leading / trailing separators, empty input
+    got, consumed, bad = _parse(H, b"  \n 7 ,8\n\n", 10, 8)
+    assert list(got) == [7.0, 8.0] and consumed == 10 and bad == 0
+    got, consumed, bad = _parse(H, b"", 10, 8)
+    assert len(got) == 0 and bad == 0
+
+
 def _compare_protocol(out_text, golden_path, nt, nheader, nr=None):
     got = out_text.split("\n")
     ref = open(golden_path).read().split("\n")
