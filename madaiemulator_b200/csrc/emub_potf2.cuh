@@ -26,14 +26,41 @@
 
 namespace emub {
 
-constexpr int POTF2_THREADS = 192;   // 136 sub-block owners in warps 0-4, warp 5 factorises the diagonal sub-blocks
+// 8 warps = 2 per warp scheduler (scheduler = warp id mod 4).  The 136 sub-block owners fill warps 0-3 and a quarter
+// of warp 4; warp 7 factorises the diagonal sub-blocks: it shares its scheduler with warp 3, whose sub-blocks (block
+// rows 3-8) retire first, so that for the second half of the sweep the dependent FP64 chain of step A does not queue
+// behind an owner's DFMA stream (8.4 -> 13 cycles per dependent DFMA with a streaming warp on the same scheduler,
+// tools/fp64_contention.cu).  Warps 5 and 6 only take part in step B.
+constexpr int POTF2_THREADS = 256;
 constexpr int POTF2_NBLOCKS = 136;
-constexpr int POTF2_HELPER0 = 160;
+constexpr int POTF2_HELPER0 = 224;    // first thread of the helper warp (warp 7)
 constexpr int POTF2_LPACK = TB * (TB + 1) / 2;
-constexpr int POTF2_LS = 9;          // row stride of the L panel (conflict-free column reads)
-constexpr int POTF2_VS = TB + 8;     // row stride of the V panel
-constexpr int POTF2_SMEM_DOUBLES = POTF2_LPACK + 2 * TB * POTF2_LS + 2 * 8 * POTF2_VS + 6 * 64 + TB;
+// Shared-memory layouts of the two panels, chosen so that the sub-block owners of one warp (same k, up to 16
+// different block rows / block columns) hit different banks:
+//   L panel: row i at i * 9 + (i >> 3); rows of consecutive block rows are 73 doubles apart (146 words = 18 mod 32)
+//   V panel: row k at k * 160, column g at (g >> 3) * 10 + (g & 7); the 8-column groups of consecutive block columns
+//            are 80 bytes apart, so the 16-byte loads of a quarter warp cover all 32 banks once
+constexpr int POTF2_LS = 9;
+constexpr int POTF2_LPANEL = TB * POTF2_LS + TB / 8;
+constexpr int POTF2_VS = (TB / 8) * 10;
+__device__ __forceinline__ int potf2_lrow(int i) { return i * POTF2_LS + (i >> 3); }
+__device__ __forceinline__ int potf2_vcol(int g) { return (g >> 3) * 10 + (g & 7); }
+constexpr int POTF2_SMEM_DOUBLES = POTF2_LPACK + 2 * POTF2_LPANEL + 2 * 8 * POTF2_VS + 6 * 64 + TB;
 constexpr int POTF2_SMEM_BYTES = POTF2_SMEM_DOUBLES * 8;
+
+// 1 / sqrt(x) for a normal, positive x without the library routine's special-case branch: hardware seed (2^-22) and two
+// Newton steps, about one ulp
+__device__ __forceinline__ double potf2_rsqrt(double x)
+{
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+	for (int it = 0; it < 2; it++) {
+		const double e = fma(-(x * y), y, 1.0);
+		y = fma(0.5 * y, e, y);
+	}
+	return y;
+}
 
 // Step A for panel q, by the helper warp: D = parked diagonal sub-block (updated through panel q - 2) minus the
 // rank-8 contribution of panel q - 1 (its rows of L are final in LPprev), then D = L_D L_D^T, W_D = L_D^-1.
@@ -47,7 +74,7 @@ __device__ __forceinline__ void potf2_diag_block(int q, int lane, const double *
 		const int e = lane + 32 * h, r = e >> 3, c = e & 7;
 		double v = Dpark[e];
 		if (LPprev) {
-			const double *lr = LPprev + (q * 8 + r) * POTF2_LS, *lc = LPprev + (q * 8 + c) * POTF2_LS;
+			const double *lr = LPprev + potf2_lrow(q * 8 + r), *lc = LPprev + potf2_lrow(q * 8 + c);
 #pragma unroll
 			for (int k = 0; k < 8; k++) v -= lr[k] * lc[k];
 		}
@@ -55,7 +82,11 @@ __device__ __forceinline__ void potf2_diag_block(int q, int lane, const double *
 	}
 	__syncwarp();
 	if (lane == 0) {
-		double a[8][8], isqv[8];
+		// One thread, everything in registers, no branch inside: the only long dependent chain is pivot -> rsqrt ->
+		// column scale -> update -> next pivot.  Row j of the inverse (forward substitution,
+		// W(j,c) = -W(j,j) sum_{c <= k < j} L(j,k) W(k,c)) needs nothing from step j but the final scaling, so its
+		// sums sit in the shadow of the reciprocal square root.
+		double a[8][8], w[8][8];
 #pragma unroll
 		for (int r = 0; r < 8; r++)
 #pragma unroll
@@ -63,11 +94,18 @@ __device__ __forceinline__ void potf2_diag_block(int q, int lane, const double *
 #pragma unroll
 		for (int j = 0; j < 8; j++) {
 			double pv = a[j][j];
-			const bool ok = (pv > 0.0) && (pv < 1.0e300);
+			const bool ok = (pv > 1.0e-290) && (pv < 1.0e300);
 			if (!ok) { *s_bad = 1; pv = 1.0; }
 			pivots[q * 8 + j] = pv;
-			const double isq = rsqrt(pv);
-			isqv[j] = isq;
+			const double isq = potf2_rsqrt(pv);
+			double t[8];
+#pragma unroll
+			for (int c = 0; c < j; c++) {
+				double sum = 0.0;
+#pragma unroll
+				for (int k = c; k < j; k++) sum += a[j][k] * w[k][c];
+				t[c] = sum;
+			}
 			a[j][j] = pv * isq;
 #pragma unroll
 			for (int i = j + 1; i < 8; i++) a[i][j] *= isq;
@@ -75,28 +113,17 @@ __device__ __forceinline__ void potf2_diag_block(int q, int lane, const double *
 			for (int i = j + 1; i < 8; i++)
 #pragma unroll
 				for (int c = j + 1; c <= i; c++) a[i][c] -= a[i][j] * a[c][j];
+			w[j][j] = isq;
+#pragma unroll
+			for (int c = 0; c < j; c++) w[j][c] = -t[c] * isq;
 		}
 #pragma unroll
 		for (int r = 0; r < 8; r++)
 #pragma unroll
-			for (int c = 0; c <= r; c++) Dwork[64 + r * 8 + c] = a[r][c];  // L_D
-		// in-place inverse of the lower triangle (column by column from the right)
-#pragma unroll
-		for (int j = 7; j >= 0; j--) {
-			const double ajj = isqv[j];
-#pragma unroll
-			for (int i = 7; i > j; i--) {
-				double t = 0.0;
-#pragma unroll
-				for (int k = j + 1; k <= i; k++) t += a[i][k] * a[k][j];
-				a[i][j] = -t * ajj;
+			for (int c = 0; c <= r; c++) {
+				Dwork[64 + r * 8 + c] = a[r][c];  // L_D
+				Dwork[r * 8 + c] = w[r][c];       // W_D
 			}
-			a[j][j] = ajj;
-		}
-#pragma unroll
-		for (int r = 0; r < 8; r++)
-#pragma unroll
-			for (int c = 0; c <= r; c++) Dwork[r * 8 + c] = a[r][c];  // W_D
 	}
 	__syncwarp();
 #pragma unroll
@@ -104,7 +131,7 @@ __device__ __forceinline__ void potf2_diag_block(int q, int lane, const double *
 		const int e = lane + 32 * h, r = e >> 3, c = e & 7;
 		const double w = (c <= r) ? Dwork[e] : 0.0;
 		WD[e] = w;
-		VR[r * POTF2_VS + q * 8 + c] = w;
+		VR[r * POTF2_VS + q * 10 + c] = w;
 		if (c <= r) {
 			const int gi = q * 8 + r;
 			Lp[gi * (gi + 1) / 2 + q * 8 + c] = Dwork[64 + e];
@@ -119,7 +146,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 	extern __shared__ __align__(16) double sm[];
 	double *Lp = sm;                                   // packed lower triangle of L: (i, c) at i (i + 1) / 2 + c
 	double *Lpanel = Lp + POTF2_LPACK;                 // [2][128][9]   L(i, 8p + k)
-	double *Vrow = Lpanel + 2 * TB * POTF2_LS;         // [2][8][136]   rows J of the inverse in progress
+	double *Vrow = Lpanel + 2 * POTF2_LPANEL;          // [2][8][160]   rows J of the inverse in progress
 	double *Dbuf = Vrow + 2 * 8 * POTF2_VS;            // [2][8][8]     W_D
 	double *Dpark = Dbuf + 2 * 64;                     // [2][8][8]     diagonal sub-block q, updated through panel q - 2
 	double *Dwork = Dpark + 2 * 64;                    // [2][8][8]     helper scratch
@@ -130,13 +157,14 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 	const double *A = Abase + b * strideA + blk;
 	double *Lg = Lbase + b * strideL + blk;
 	double *Wg = Wbase + b * strideW + blk;
-	const bool active = tid < POTF2_NBLOCKS;
 	const bool helper = tid >= POTF2_HELPER0;
-	// sub-block t = 135 - tid in row-major triangular order: warp 0 holds the last block rows (live until the end),
-	// warp 4 only the 8 sub-blocks of the first rows (retired after 4 panels) -- warps 0 and 4 share a scheduler
+	const int oslot = tid;
+	const bool active = oslot < POTF2_NBLOCKS;
+	// sub-block t = 135 - slot in row-major triangular order: the first slots hold the last block rows (live until the
+	// end), the last ones the sub-blocks of the first rows (retired after a few panels)
 	int bi = 0, bj = 0;
 	if (active) {
-		const int t = POTF2_NBLOCKS - 1 - tid;
+		const int t = POTF2_NBLOCKS - 1 - oslot;
 		while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
 		bj = t - bi * (bi + 1) / 2;
 	}
@@ -164,7 +192,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 #pragma unroll
 			for (int r = 0; r < 8; r++)
 #pragma unroll
-				for (int k = 0; k < 8; k++) { Lpanel[(bi * 8 + r) * POTF2_LS + k] = a[r][k]; a[r][k] = 0.0; }
+				for (int k = 0; k < 8; k++) { Lpanel[potf2_lrow(bi * 8 + r) + k] = a[r][k]; a[r][k] = 0.0; }
 		}
 	}
 	// strictly upper sub-blocks of both outputs are zero
@@ -179,22 +207,19 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 	if (helper) potf2_diag_block(0, tid - POTF2_HELPER0, Dpark, nullptr, Dwork, Dbuf, Vrow, Lp, pivots, &s_bad);
 
 #ifdef EMUB_POTF2_TIMING
-	long long tB = 0, tCA = 0, tlast = clock64(), tstart = tlast;
+	// per panel and warp: clock at arrival at barrier 1 and at barrier 2 (lane 0 of every warp; ptxas hoists a clock
+	// read above the barrier that precedes it, so "after the barrier" cannot be stamped)
+	__shared__ long long s_clk[16][8][2];
+#define POTF2_STAMP(slot) do { if ((tid & 31) == 0) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); s_clk[p][tid >> 5][slot] = t_; } } while (0)
+#else
+#define POTF2_STAMP(slot) do { } while (0)
 #endif
 	for (int p = 0; p < 16; p++) {
-		double *LP = Lpanel + (p & 1) * TB * POTF2_LS;
+		double *LP = Lpanel + (p & 1) * POTF2_LPANEL;
 		double *VR = Vrow + (p & 1) * 8 * POTF2_VS;
 		double *WD = Dbuf + (p & 1) * 64;
-#ifdef EMUB_POTF2_TIMING
-		if ((tid & 31) == 0 && b == 0) logdet_parts[128 + p * 8 + (tid >> 5)] = (double)(clock64() - tstart);
-#endif
+		POTF2_STAMP(0);
 		__syncthreads();  // W_D(p), L_D(p) are there (helper warp, during the previous rank-8 update)
-#ifdef EMUB_POTF2_TIMING
-		if (tid == 0 && b == 0) logdet_parts[128 + p * 8 + 6] = (double)(clock64() - tstart);
-#endif
-#ifdef EMUB_POTF2_TIMING
-		{ long long t = clock64(); tCA += t - tlast; tlast = t; }
-#endif
 		// ---- B: all threads share the two small transforms against W_D ------------------------------------------------
 		{
 			// the 36 entries of W_D first, as independent loads (otherwise every FMA below waits for its own load)
@@ -208,7 +233,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 			if (gi < TB) {
 				double pr[8], lr[8];
 #pragma unroll
-				for (int c = 0; c < 8; c++) pr[c] = LP[gi * POTF2_LS + c];
+				for (int c = 0; c < 8; c++) pr[c] = LP[potf2_lrow(gi) + c];
 #pragma unroll
 				for (int k = 0; k < 8; k++) {
 					double s = 0.0;
@@ -219,8 +244,8 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 				const int base = gi * (gi + 1) / 2 + p * 8;
 #pragma unroll
 				for (int k = 0; k < 8; k++) {
-					LP[gi * POTF2_LS + k] = lr[k];
-					VR[k * POTF2_VS + gi] = lr[k];  // the same column of L as the right factor V(k, gi) of the rank-8 update
+					LP[potf2_lrow(gi) + k] = lr[k];
+					VR[k * POTF2_VS + potf2_vcol(gi)] = lr[k];  // the same column of L as the right factor V(k, gi) of the rank-8 update
 					Lp[base + k] = lr[k];
 				}
 			}
@@ -229,20 +254,18 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 			if (gc < p * 8) {
 				double er[8];
 #pragma unroll
-				for (int k = 0; k < 8; k++) er[k] = VR[k * POTF2_VS + gc];
+				for (int k = 0; k < 8; k++) er[k] = VR[k * POTF2_VS + potf2_vcol(gc)];
 #pragma unroll
 				for (int r = 0; r < 8; r++) {
 					double s = 0.0;
 #pragma unroll
 					for (int k = 0; k <= r; k++) s += w[r * (r + 1) / 2 + k] * er[k];
-					VR[r * POTF2_VS + gc] = s;
+					VR[r * POTF2_VS + potf2_vcol(gc)] = s;
 				}
 			}
 		}
+		POTF2_STAMP(1);
 		__syncthreads();
-#ifdef EMUB_POTF2_TIMING
-		{ long long t = clock64(); tB += t - tlast; tlast = t; }
-#endif
 		// ---- C: rank-8 update of every row below the panel; the owners of rows J pick up their final values; the
 		//         helper warp factorises the next diagonal sub-block at the same time ------------------------------------
 		if (helper) {
@@ -250,8 +273,8 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 				potf2_diag_block(p + 1, tid - POTF2_HELPER0, Dpark + ((p + 1) & 1) * 64, LP, Dwork, Dbuf + ((p + 1) & 1) * 64,
 				                 Vrow + ((p + 1) & 1) * 8 * POTF2_VS, Lp, pivots, &s_bad);
 		} else if (active && bi > p) {
-			const double *lrow = LP + bi * 8 * POTF2_LS;
-			const double *vcol = VR + bj * 8;
+			const double *lrow = LP + potf2_lrow(bi * 8);
+			const double *vcol = VR + bj * 10;
 #pragma unroll
 			for (int k = 0; k < 8; k++) {
 				double l[8], v[8];
@@ -271,19 +294,19 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 			// park the raw data of the coming panels in the other halves of the buffers (their last readers are two
 			// barriers behind) and clear the slots that start to hold the inverse
 			if (p + 1 < 16) {
-				double *LPn = Lpanel + ((p + 1) & 1) * TB * POTF2_LS;
+				double *LPn = Lpanel + ((p + 1) & 1) * POTF2_LPANEL;
 				double *VRn = Vrow + ((p + 1) & 1) * 8 * POTF2_VS;
 				if (bj == p + 1 && bi > p + 1) {
 #pragma unroll
 					for (int r = 0; r < 8; r++)
 #pragma unroll
-						for (int k = 0; k < 8; k++) { LPn[(bi * 8 + r) * POTF2_LS + k] = a[r][k]; a[r][k] = 0.0; }
+						for (int k = 0; k < 8; k++) { LPn[potf2_lrow(bi * 8 + r) + k] = a[r][k]; a[r][k] = 0.0; }
 				}
 				if (bi == p + 1 && bj <= p) {
 #pragma unroll
 					for (int k = 0; k < 8; k++)
 #pragma unroll
-						for (int c = 0; c < 8; c++) VRn[k * POTF2_VS + bj * 8 + c] = a[k][c];
+						for (int c = 0; c < 8; c++) VRn[k * POTF2_VS + bj * 10 + c] = a[k][c];
 				}
 				if (bi == p + 2 && bj == p + 2) {
 #pragma unroll
@@ -294,7 +317,7 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 			}
 		} else if (active && bi == p) {
 			// rows J are final: from VR (left of the panel) or W_D (the diagonal sub-block)
-			const double *src = (bj < p) ? (VR + bj * 8) : nullptr;
+			const double *src = (bj < p) ? (VR + bj * 10) : nullptr;
 #pragma unroll
 			for (int k = 0; k < 8; k++)
 #pragma unroll
@@ -304,9 +327,8 @@ __global__ void __launch_bounds__(POTF2_THREADS) k_potf2(const double *Abase, lo
 	}
 	__syncthreads();
 #ifdef EMUB_POTF2_TIMING
-	if (tid == POTF2_HELPER0 - 1 && b == 0) {
-		logdet_parts[64] = (double)tCA; logdet_parts[65] = (double)tB; logdet_parts[66] = (double)(clock64() - tstart);
-	}
+	if (b == 0)
+		for (int idx = tid; idx < 16 * 8 * 2; idx += POTF2_THREADS) logdet_parts[128 + idx] = (double)((&s_clk[0][0][0])[idx] - s_clk[0][0][0]);
 #endif
 	double logsum = 0.0;
 	if (tid < 32) {

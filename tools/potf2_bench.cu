@@ -19,7 +19,7 @@ int main(int argc, char **argv)
 			}
 	double *dA, *dL, *dW, *dlog; int *dinfo;
 	size_t bytes = A.size() * 8;
-	CK(cudaMalloc(&dA, bytes)); CK(cudaMalloc(&dL, bytes)); CK(cudaMalloc(&dW, bytes)); CK(cudaMalloc(&dlog, (B + 512) * 8)); CK(cudaMalloc(&dinfo, B * 4));
+	CK(cudaMalloc(&dA, bytes)); CK(cudaMalloc(&dL, bytes)); CK(cudaMalloc(&dW, bytes)); CK(cudaMalloc(&dlog, (B + 1024) * 8)); CK(cudaMalloc(&dinfo, B * 4));
 	CK(cudaMemcpy(dA, A.data(), bytes, cudaMemcpyHostToDevice));
 	CK(cudaMemset(dinfo, 0, B * 4));
 	CK(cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
@@ -43,14 +43,14 @@ int main(int argc, char **argv)
 	}
 #ifdef EMUB_POTF2_TIMING
 	{
-		double tk[3];
-		CK(cudaMemcpy(tk, dlog + 64, sizeof(tk), cudaMemcpyDeviceToHost));
-		printf("cycles: C(p-1)+A(p) %.0f | B %.0f | sweep total %.0f\n", tk[0], tk[1], tk[2]);
-		double arr[128];
-		CK(cudaMemcpy(arr, dlog + 128, sizeof(arr), cudaMemcpyDeviceToHost));
+		const int NW = POTF2_THREADS / 32;
+		std::vector<double> clk(16 * 8 * 2);
+		CK(cudaMemcpy(clk.data(), dlog + 128, clk.size() * 8, cudaMemcpyDeviceToHost));
+		printf("cycles since the first stamp, per warp: arrival at barrier 1 (previous C / A done) | arrival at barrier 2 (B done)\n");
 		for (int p = 0; p < 16; p++) {
-			printf("panel %2d arrivals at barrier 1 (cycles since sweep start): w0 %6.0f w1 %6.0f w2 %6.0f w3 %6.0f w4 %6.0f helper %6.0f | released %6.0f\n", p,
-			       arr[p * 8], arr[p * 8 + 1], arr[p * 8 + 2], arr[p * 8 + 3], arr[p * 8 + 4], arr[p * 8 + 5], arr[p * 8 + 6]);
+			printf("panel %2d:", p);
+			for (int w = 0; w < NW; w++) printf("  w%d %6.0f %6.0f", w, clk[(p * 8 + w) * 2], clk[(p * 8 + w) * 2 + 1]);
+			printf("\n");
 		}
 	}
 #endif
