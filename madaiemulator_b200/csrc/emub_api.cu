@@ -43,6 +43,16 @@ static int set_err(int code, const char *fmt, const char *a = "", int line = 0)
 		if (e__ != cudaSuccess) return set_err(EMUB_ECUDA, "CUDA: %s (emub_api.cu:%d)", cudaGetErrorString(e__), __LINE__); \
 	} while (0)
 
+// device scratch that lives for one call: released on every return path
+struct ScopedDev {
+	double *p = nullptr;
+	~ScopedDev() { if (p) cudaFree(p); }
+	cudaError_t alloc(size_t doubles) { return cudaMalloc(&p, sizeof(double) * (doubles ? doubles : 1)); }
+	ScopedDev() = default;
+	ScopedDev(const ScopedDev &) = delete;
+	ScopedDev &operator=(const ScopedDev &) = delete;
+};
+
 static const char *k_family_names[EMUB_K_NFAMILIES] = {"cov", "potf2", "gemm_chol", "gemm_trtri", "gemm_lauum", "skinny",
                                                        "small", "grad", "kcross", "gemm_pred", "pred_final"};
 
@@ -399,8 +409,9 @@ extern "C" int emub_model_set_training_multi(emub_model *m, const double *Y, int
 	CUDA_TRY(cudaSetDevice(m->ctx->device));
 	CUDA_TRY(cudaDeviceSynchronize());
 	cudaStream_t st = m->ctx->streams[0];
-	double *dY = nullptr;
-	CUDA_TRY(cudaMalloc(&dY, sizeof(double) * (size_t)m->n * ncomp));
+	ScopedDev sY;
+	CUDA_TRY(sY.alloc((size_t)m->n * ncomp));
+	double *dY = sY.p;
 	CUDA_TRY(cudaMemcpy2D(dY, sizeof(double) * ncomp, Y, sizeof(double) * ldy, sizeof(double) * ncomp, m->n, cudaMemcpyHostToDevice));
 	// captured graphs hold the address of dYh: drop them whenever the training data is rebuilt
 	for (auto &g : m->graphs) cudaGraphExecDestroy(g.second);
@@ -408,9 +419,11 @@ extern "C" int emub_model_set_training_multi(emub_model *m, const double *Y, int
 	m->graph_launches.clear();
 	if (ncomp != m->ncomp) {
 		cudaFree(m->dYh);
+		m->dYh = nullptr;
+		m->ncomp = 0;
+		free_query_ws(m);
 		CUDA_TRY(cudaMalloc(&m->dYh, sizeof(double) * (size_t)ncomp * m->npad * m->ncp));
 		m->ncomp = ncomp;
-		free_query_ws(m);
 	}
 	for (int c = 0; c < ncomp; c++) {
 		LaunchScope ls(m->ctx, EMUB_K_SMALL, 0, st);
@@ -419,7 +432,6 @@ extern "C" int emub_model_set_training_multi(emub_model *m, const double *Y, int
 	}
 	CUDA_TRY(cudaStreamSynchronize(st));
 	CUDA_TRY(cudaGetLastError());
-	cudaFree(dY);
 	return EMUB_OK;
 }
 
@@ -774,9 +786,10 @@ extern "C" int emub_k_vectors(emub_model *m, const double *thetas, const double 
 	CUDA_TRY(cudaSetDevice(c->device));
 	cudaStream_t st = c->streams[0];
 	const int mq_pad = (mq + TB - 1) / TB * TB;
-	double *dQ = nullptr, *dK = nullptr;
-	CUDA_TRY(cudaMalloc(&dQ, sizeof(double) * (size_t)mq_pad * m->d));
-	CUDA_TRY(cudaMalloc(&dK, sizeof(double) * (size_t)m->npad * mq_pad));
+	ScopedDev sQ, sK;
+	CUDA_TRY(sQ.alloc((size_t)mq_pad * m->d));
+	CUDA_TRY(sK.alloc((size_t)m->npad * mq_pad));
+	double *dQ = sQ.p, *dK = sK.p;
 	CUDA_TRY(cudaMemcpy2DAsync(dQ, sizeof(double) * m->d, pts, sizeof(double) * ldp, sizeof(double) * m->d, mq, cudaMemcpyHostToDevice, st));
 	CUDA_TRY(cudaMemcpyAsync(m->dThetas, thetas, sizeof(double) * m->nth, cudaMemcpyHostToDevice, st));
 	{
@@ -786,7 +799,6 @@ extern "C" int emub_k_vectors(emub_model *m, const double *thetas, const double 
 	launch_kcross(m, st, m->dConsts, dQ, mq, mq_pad, dK, mq_pad);
 	CUDA_TRY(cudaMemcpy2DAsync(K, sizeof(double) * ldk, dK, sizeof(double) * mq_pad, sizeof(double) * mq, m->n, cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(cudaStreamSynchronize(st));
-	cudaFree(dQ); cudaFree(dK);
 	CUDA_TRY(cudaGetLastError());
 	return EMUB_OK;
 }
@@ -805,9 +817,10 @@ extern "C" int emub_debug_exp(emub_ctx *c, const double *x, int n, double *out)
 {
 	if (!c || !x || !out || n < 1) return set_err(EMUB_EINVAL, "emub_debug_exp: bad argument%s");
 	CUDA_TRY(cudaSetDevice(c->device));
-	double *dx = nullptr, *dout = nullptr;
-	CUDA_TRY(cudaMalloc(&dx, sizeof(double) * n));
-	CUDA_TRY(cudaMalloc(&dout, sizeof(double) * n));
+	ScopedDev sx, sout;
+	CUDA_TRY(sx.alloc((size_t)n));
+	CUDA_TRY(sout.alloc((size_t)n));
+	double *dx = sx.p, *dout = sout.p;
 	CUDA_TRY(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
 	{
 		LaunchScope ls(c, EMUB_K_SMALL, 0, c->streams[0]);
@@ -815,7 +828,6 @@ extern "C" int emub_debug_exp(emub_ctx *c, const double *x, int n, double *out)
 	}
 	CUDA_TRY(cudaStreamSynchronize(c->streams[0]));
 	CUDA_TRY(cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
-	cudaFree(dx); cudaFree(dout);
 	return EMUB_OK;
 }
 
