@@ -65,6 +65,15 @@ int emub_model_set_training(emub_model *m, const double *y);
  * multivariate model (multi_modelstruct.c:295-316); component c is column c */
 int emub_model_set_training_multi(emub_model *m, const double *Y, int ldy, int ncomp);
 int emub_model_ncomponents(const emub_model *m);
+/* Which gradient the batch entry points return.  EMUB_GRAD_LITERAL (default): the reference's formula, gradFnMulti /
+ * getGradientCn (maxmultimin.c:416-608) -- raw y instead of the residual, the k-th factor of the kernel only, a
+ * sigma^2 factor; it is NOT the gradient of what evalFnMulti returns.  EMUB_GRAD_EXACT (deviation
+ * D-4, optional): the true gradient of that objective, d(-L)/dtheta = 1/2 tr(C^-1 dC) - 1/2 z^T dC z with
+ * z = C^-1 (y - H beta); used by the optional refinement run of the restart driver (emub_estimate.h).  The nugget
+ * derivative is taken on the diagonal only, like the reference (:520-522). */
+enum { EMUB_GRAD_LITERAL = 0, EMUB_GRAD_EXACT = 1 };
+int emub_model_set_gradient_mode(emub_model *m, int mode);
+int emub_model_gradient_mode(const emub_model *m);
 
 /* makeCovMatrix_fnptr (emulator.c:636): C (n x n, row stride ldc) at the FULL theta vector */
 int emub_cov_matrix(emub_model *m, const double *thetas, double *C, int ldc);

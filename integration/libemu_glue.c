@@ -13,7 +13,8 @@
  *
  * Engine handles are kept in side tables keyed by the reference's struct pointers, so no reference
  * struct changes.  Environment: EMUB_DEVICE (default 0), EMUB_SLOTS (in-flight evaluations per model,
- * default 8), EMUB_TRIES (restarts of estimate_thetas_threaded, default 50 x ncpus like the reference).
+ * default 8), EMUB_TRIES (restarts of estimate_thetas_threaded, default 50 x ncpus like the reference),
+ * EMUB_POLISH (iterations of the refinement run from the best restart, default 100, 0 = the reference's stop rule only).
  */
 #include <math.h>
 #include <pthread.h>
@@ -159,6 +160,7 @@ void estimate_thetas_threaded(modelstruct *the_model, optstruct *options)
 	emub_estimate_default_opts(&o);
 	o.max_tries = env_int("EMUB_TRIES", 50 * (int)(ncpus > 0 ? ncpus : 1)); /* estimate_threaded.c:97-113 */
 	o.nchains = env_int("EMUB_SLOTS", 8);
+	o.polish_steps = env_int("EMUB_POLISH", 100); /* refinement run from the best restart (emub_estimate.h); 0 = off */
 	FILE *ur = fopen("/dev/urandom", "rb"); /* useful.c:49 */
 	if (ur) { if (fread(&o.seed, sizeof(o.seed), 1, ur) != 1) o.seed = 1; fclose(ur); }
 	if (getenv("EMUB_SEED")) o.seed = strtoull(getenv("EMUB_SEED"), NULL, 10);

@@ -102,6 +102,7 @@ struct emub_model {
 	size_t mat;  // npad * npad
 	double *dX, *dy, *dYh;  // dYh: ncomp x npad x ncp
 	int ncomp;              // training vectors sharing the design (PCA components, multi_modelstruct.c:121-148)
+	int exact_grad;         // 0: the reference's literal gradient formula; 1: the true gradient of the objective (D-4)
 	int *dComp, *hComp;     // component evaluated by each slot of the current chunk
 	struct QueryWs *qws;    // query workspace shared by every emulator of this model (lazily allocated)
 	GemmTask *dTasks;
@@ -437,6 +438,14 @@ extern "C" int emub_model_set_training_multi(emub_model *m, const double *Y, int
 
 extern "C" int emub_model_ncomponents(const emub_model *m) { return m ? m->ncomp : 0; }
 
+extern "C" int emub_model_set_gradient_mode(emub_model *m, int mode)
+{
+	if (!m || (mode != EMUB_GRAD_LITERAL && mode != EMUB_GRAD_EXACT)) return set_err(EMUB_EINVAL, "emub_model_set_gradient_mode: bad argument%s");
+	m->exact_grad = mode == EMUB_GRAD_EXACT;
+	return EMUB_OK;
+}
+extern "C" int emub_model_gradient_mode(const emub_model *m) { return (m && m->exact_grad) ? EMUB_GRAD_EXACT : EMUB_GRAD_LITERAL; }
+
 extern "C" int emub_model_set_training(emub_model *m, const double *y)
 {
 	if (!m || !y) return set_err(EMUB_EINVAL, "emub_model_set_training: null%s");
@@ -573,16 +582,27 @@ static void run_gradient(emub_model *m, cudaStream_t st, int s0, int count)
 	{
 		LaunchScope ls(c, EMUB_K_GRAD, count * 4.0 * (double)m->mat, st);
 		dim3 grid(nt64, nt64, count);
-		switch (m->kernel) {
-		case 2: k_grad_tiles<2><<<grid, 256, smem, st>>>(Cinv, (long long)m->mat, m->npad, AB, sUG, m->ncp, m->dX, m->n, m->d, consts, part, nt64); break;
-		case 3: k_grad_tiles<3><<<grid, 256, smem, st>>>(Cinv, (long long)m->mat, m->npad, AB, sUG, m->ncp, m->dX, m->n, m->d, consts, part, nt64); break;
-		default: k_grad_tiles<1><<<grid, 256, smem, st>>>(Cinv, (long long)m->mat, m->npad, AB, sUG, m->ncp, m->dX, m->n, m->d, consts, part, nt64); break;
+		const double *res = m->dRes + (size_t)s0 * RES_STRIDE;
+#define EMUB_GRAD_LAUNCH(KN, EX) k_grad_tiles<KN, EX><<<grid, 256, smem, st>>>(Cinv, (long long)m->mat, m->npad, AB, sUG, m->ncp, m->dX, m->n, m->d, consts, part, nt64, res, m->p)
+		if (m->exact_grad) {
+			switch (m->kernel) {
+			case 2: EMUB_GRAD_LAUNCH(2, true); break;
+			case 3: EMUB_GRAD_LAUNCH(3, true); break;
+			default: EMUB_GRAD_LAUNCH(1, true); break;
+			}
+		} else {
+			switch (m->kernel) {
+			case 2: EMUB_GRAD_LAUNCH(2, false); break;
+			case 3: EMUB_GRAD_LAUNCH(3, false); break;
+			default: EMUB_GRAD_LAUNCH(1, false); break;
+			}
 		}
+#undef EMUB_GRAD_LAUNCH
 	}
 	{
 		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
 		k_grad_final<<<count, 256, 0, st>>>(part, nt64, Cinv, (long long)m->mat, m->npad, AB, sUG, m->ncp, m->n, m->d, m->kernel, consts,
-		                                    m->dRes + (size_t)s0 * RES_STRIDE);
+		                                    m->dRes + (size_t)s0 * RES_STRIDE, m->exact_grad, m->p);
 	}
 }
 
@@ -642,7 +662,8 @@ static int run_chunk(emub_model *m, int count, int nth_in, int mode, int want_gr
 		return EMUB_OK;
 	}
 	const unsigned long long key = ((unsigned long long)count << 32) | ((unsigned)nth_in << 16) | ((unsigned)ng << 8) |
-	                               ((unsigned)mode << 2) | ((unsigned)(want_grad != 0) << 1) | (unsigned)(emulator_mode != 0);
+	                               ((unsigned)(m->exact_grad != 0) << 4) | ((unsigned)mode << 2) | ((unsigned)(want_grad != 0) << 1) |
+	                               (unsigned)(emulator_mode != 0);
 	cudaGraphExec_t exec = nullptr;
 	for (auto &g : m->graphs)
 		if (g.first == key) { exec = g.second; break; }

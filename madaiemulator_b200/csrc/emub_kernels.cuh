@@ -432,11 +432,16 @@ __global__ void __launch_bounds__(256) k_small(const double *__restrict__ part, 
 // Matern (deviation D-3): one slot, (alpha_i alpha_j - Cinv_ij) * f(t), t = root * r / rho.
 // dC/dtheta is never stored.  grid (npad/64, npad/64, B) (upper tiles exit), 256 threads,
 // dynamic smem (2*d*64 + 2*64) doubles.
-template <int KERNEL>
+// EXACT (deviation D-4, optional): the true gradient of the objective evalFnMulti returns,
+//   d(-L)/dtheta = 1/2 tr(C^-1 dC) - 1/2 z^T dC z,  z = C^-1 (y - H beta),  dC_ij/dtheta_k = c_ij q_k exp(-2 theta_k)
+// i.e. the same sums with z for alpha (res: beta from k_small) and the full product kernel c_ij for its k-th factor --
+// one exp per pair instead of d.  The literal formula stays the default.
+template <int KERNEL, bool EXACT>
 __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ Cbase, long long strideC, int ld,
                                                     const double *__restrict__ ABbase, long long strideAB, int ncp,
                                                     const double *__restrict__ X, int n, int d,
-                                                    const double *__restrict__ consts, double *__restrict__ part, int ntiles64)
+                                                    const double *__restrict__ consts, double *__restrict__ part, int ntiles64,
+                                                    const double *__restrict__ res, int p)
 {
 	const int bj = blockIdx.x, bi = blockIdx.y, b = blockIdx.z;
 	if (bj > bi) return;
@@ -457,8 +462,15 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 		sXj[k * CT + r] = (j0 + r < n) ? X[(size_t)(j0 + r) * d + k] : 0.0;
 	}
 	const double *AB = ABbase + b * strideAB;
-	if (tid < CT) sAi[tid] = AB[(size_t)(i0 + tid) * ncp];
-	else if (tid < 2 * CT) sAj[tid - CT] = AB[(size_t)(j0 + tid - CT) * ncp];
+	if (tid < 2 * CT) {
+		const double *row = AB + (size_t)((tid < CT) ? i0 + tid : j0 + tid - CT) * ncp;
+		double a = row[0];
+		if (EXACT) {  // z = alpha - (C^-1 H) beta
+			const double *beta = res + (size_t)b * RES_STRIDE + RES_BETA;
+			for (int c = 0; c < p; c++) a -= row[1 + c] * beta[c];
+		}
+		if (tid < CT) sAi[tid] = a; else sAj[tid - CT] = a;
+	}
 	__syncthreads();
 	const int tx = tid & 15, ty = tid >> 4;
 	const double *C = Cbase + b * strideC;
@@ -475,7 +487,45 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 		}
 	}
 	const int nslots = (KERNEL == 1) ? d : 1;
-	if (KERNEL == 1) {
+	if (KERNEL == 1 && EXACT) {
+		// w <- w c_ij, the unit-amplitude kernel from its exponent sum_k a_k q_k; then one weighted sum of q_k per theta_k
+		double ex[4][4];
+#pragma unroll
+		for (int r = 0; r < 4; r++)
+#pragma unroll
+			for (int c = 0; c < 4; c++) ex[r][c] = 0.0;
+		for (int k = 0; k < d; k++) {
+			const double ak = sc[4 + d + k];
+#pragma unroll
+			for (int r = 0; r < 4; r++) {
+				const double xi = sXi[k * CT + ty + 16 * r];
+#pragma unroll
+				for (int c = 0; c < 4; c++) {
+					const double dl = xi - sXj[k * CT + tx + 16 * c];
+					ex[r][c] += ak * (dl * dl);
+				}
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < 4; r++)
+#pragma unroll
+			for (int c = 0; c < 4; c++) w[r][c] *= exp_neg(-ex[r][c], stab);
+		for (int k = 0; k < d; k++) {
+			double s = 0.0;
+#pragma unroll
+			for (int r = 0; r < 4; r++) {
+				const double xi = sXi[k * CT + ty + 16 * r];
+#pragma unroll
+				for (int c = 0; c < 4; c++) {
+					const double dl = xi - sXj[k * CT + tx + 16 * c];
+					s += w[r][c] * (dl * dl);
+				}
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+			if (lane == 0) red[warp][k] = s;
+		}
+	} else if (KERNEL == 1) {
 		for (int k = 0; k < d; k++) {
 			const double ak = sc[4 + d + k];
 			double s = 0.0;
@@ -532,7 +582,7 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 __global__ void __launch_bounds__(256) k_grad_final(const double *__restrict__ part, int ntiles64, const double *__restrict__ Cbase,
                                                     long long strideC, int ld, const double *__restrict__ ABbase, long long strideAB,
                                                     int ncp, int n, int d, int kernel, const double *__restrict__ consts,
-                                                    double *__restrict__ res)
+                                                    double *__restrict__ res, int exact, int p)
 {
 	__shared__ double scratch[8];
 	const int b = blockIdx.x, tid = threadIdx.x;
@@ -544,6 +594,8 @@ __global__ void __launch_bounds__(256) k_grad_final(const double *__restrict__ p
 	for (int i = tid; i < n; i += 256) {
 		tr += C[(size_t)i * ld + i];
 		double a = AB[(size_t)i * ncp];
+		if (exact)
+			for (int c = 0; c < p; c++) a -= AB[(size_t)i * ncp + 1 + c] * r[RES_BETA + c];
 		aa += a * a;
 	}
 	tr = block_sum_256(tr, scratch);
@@ -552,7 +604,7 @@ __global__ void __launch_bounds__(256) k_grad_final(const double *__restrict__ p
 	const int nslots = (kernel == 1) ? d : 1;
 	const bool failed = r[2] != 0.0;
 	const double sigma2 = cg[3];
-	const double amp = exp(log(sigma2));  // maxmultimin.c:514
+	const double amp = exact ? 1.0 : exp(log(sigma2));  // maxmultimin.c:514; the objective itself has unit amplitude
 	for (int k = 0; k < nslots; k++) {
 		double s = 0.0;
 		for (size_t tix = tid; tix < ntl; tix += 256) s += part[((size_t)b * ntl + tix) * MAXD + k];

@@ -30,7 +30,7 @@ SYMBOLS = [
     "emub_ctx_create", "emub_ctx_destroy", "emub_last_error", "emub_version", "emub_ctx_stream",
     "emub_ctx_set_groups", "emub_ctx_use_graphs", "emub_model_create", "emub_model_destroy", "emub_model_nthetas",
     "emub_model_nregression_fns", "emub_model_slots", "emub_model_set_training", "emub_model_set_training_multi",
-    "emub_model_ncomponents", "emub_loglik_grad_batch_comp", "emub_emulator_create_comp", "emub_predict_multi", "emub_cov_matrix",
+    "emub_model_ncomponents", "emub_model_set_gradient_mode", "emub_model_gradient_mode", "emub_loglik_grad_batch_comp", "emub_emulator_create_comp", "emub_predict_multi", "emub_cov_matrix",
     "emub_h_matrix", "emub_k_vectors", "emub_loglik_grad_batch", "emub_loglik_grad_batch_dev",
     "emub_ctx_synchronize", "emub_loglik_extras", "emub_emulator_create", "emub_emulator_destroy",
     "emub_emulator_beta", "emub_predict_batch", "emub_predict_batch_dev", "emub_profile_enable",
@@ -66,6 +66,8 @@ def lib():
     L.emub_ctx_destroy.restype = None
     L.emub_ctx_stream.argtypes = [_vp]
     L.emub_ctx_stream.restype = _vp
+    L.emub_model_set_gradient_mode.argtypes = [_vp, _ci]
+    L.emub_model_gradient_mode.argtypes = [_vp]
     L.emub_ctx_set_groups.argtypes = [_vp, _ci]
     L.emub_ctx_use_graphs.argtypes = [_vp, _ci]
     L.emub_ctx_synchronize.argtypes = [_vp]
@@ -192,6 +194,10 @@ class Model:
         self.nthetas = self.L.emub_model_nthetas(h)
         self.p = self.L.emub_model_nregression_fns(h)
         self.slots = self.L.emub_model_slots(h)
+
+    def set_gradient_mode(self, exact):
+        """False: the reference's literal gradient formula (default); True: the true gradient of -L (deviation D-4)."""
+        _check(self.L.emub_model_set_gradient_mode(self.h, 1 if exact else 0))
 
     def set_training(self, y):
         self.y = _c(y)
@@ -334,7 +340,7 @@ def predict_multi(emulators, pts, training_mean=None, evecs=None, evals=None):
 # ---- host C layer (madaiemulator_b200/host/libemuhost.so): restart driver over the batched evaluator ----------
 HOST_LIB_PATH = os.path.join(_HERE, "host", "libemuhost.so")
 HOST_SYMBOLS = ["emub_estimate_default_opts", "emub_sample_scales", "emub_optimization_ranges", "emub_random_init",
-                "emub_estimate_thetas", "emub_estimate_thetas_from", "emub_estimate_thetas_multi", "emub_estimate_thetas_multi_devices", "emub_snapshot_load",
+                "emub_estimate_thetas", "emub_estimate_thetas_from", "emub_estimate_thetas_multi", "emub_estimate_thetas_multi_devices", "emub_estimate_thetas_multi_devices_ranges", "emub_snapshot_load",
                 "emub_snapshot_load_path", "emub_snapshot_free", "emub_multi_emulator_from_snapshot",
                 "emub_multi_emulator_destroy", "emub_multi_emulator_predict", "emub_interactive_stream", "emub_parse_doubles",
                 "emub_snapshot_save", "emub_snapshot_save_path", "emub_snapshot_from_arrays"]
@@ -343,7 +349,7 @@ HOST_SYMBOLS = ["emub_estimate_default_opts", "emub_sample_scales", "emub_optimi
 class EstimateOpts(ctypes.Structure):
     _fields_ = [("max_tries", _ci), ("nchains", _ci), ("seed", ctypes.c_ulonglong), ("step_size", ctypes.c_double),
                 ("tol", ctypes.c_double), ("eps_abs", ctypes.c_double), ("step_max", _ci), ("first_component", _ci),
-                ("component_stride", _ci)]
+                ("component_stride", _ci), ("polish_steps", _ci), ("polish_eps", ctypes.c_double)]
 
 
 class EstimateStats(ctypes.Structure):
@@ -395,9 +401,10 @@ def random_init(seed, try_index, ranges):
     return x
 
 
-def estimate_thetas(model, ranges=None, max_tries=50, nchains=0, seed=1, starts=None):
+def estimate_thetas(model, ranges=None, max_tries=50, nchains=0, seed=1, starts=None, polish_steps=0):
     """maxWithMultiMin (maxmultimin.c:47) over the batched GPU evaluator.  Returns (thetas[nthetas], best log
-    likelihood, stats dict).  starts: optional (max_tries x nthetas) explicit start points."""
+    likelihood, stats dict).  starts: optional (max_tries x nthetas) explicit start points.  polish_steps > 0 adds the
+    optional refinement run from the best point (emub_estimate.h)."""
     H = host_lib()
     if ranges is None:
         ranges = optimization_ranges(model.kernel, model.X)
@@ -407,7 +414,7 @@ def estimate_thetas(model, ranges=None, max_tries=50, nchains=0, seed=1, starts=
     if starts is not None:
         starts = _c(starts).reshape(-1, model.nthetas)
         max_tries = starts.shape[0]
-    o.max_tries, o.nchains, o.seed = max_tries, nchains, seed
+    o.max_tries, o.nchains, o.seed, o.polish_steps = max_tries, nchains, seed, polish_steps
     th = np.zeros(model.nthetas)
     best = ctypes.c_double()
     st = EstimateStats()

@@ -20,6 +20,8 @@ void emub_estimate_default_opts(emub_estimate_opts *o)
 	o->step_max = 30;
 	o->first_component = 0;
 	o->component_stride = 1;
+	o->polish_steps = 0;
+	o->polish_eps = 1e-3;
 }
 
 /* modelstruct.c:188-213 */
@@ -106,6 +108,7 @@ typedef struct front {
 	const emub_estimate_opts *opts;
 	const double *ranges;
 	const double *starts; /* optional max_tries x nthetas explicit start points */
+	int starts_per_comp;  /* starts holds max_tries rows for every component, component-major */
 	int nth, nth1, nchains;
 	pthread_mutex_t mu;
 	pthread_cond_t cv_disp, cv_done;
@@ -164,7 +167,9 @@ static void run_restart(chain_t *c, int try_index, emub_bfgs *bf)
 	const int nth = fr->nth, nth1 = fr->nth1;
 	double *x_init = (double *)malloc(sizeof(double) * (size_t)nth);
 	double *x_final = (double *)malloc(sizeof(double) * (size_t)nth1);
-	if (fr->starts) memcpy(x_init, fr->starts + (size_t)try_index * nth, sizeof(double) * (size_t)nth);
+	if (fr->starts)
+		memcpy(x_init, fr->starts + ((size_t)(fr->starts_per_comp ? c->comp * o->max_tries : 0) + (size_t)try_index) * nth,
+		       sizeof(double) * (size_t)nth);
 	else emub_random_init(c->seed, try_index, fr->ranges, nth, x_init);
 	emub_bfgs_fn fn = {(size_t)nth1, cb_f, cb_df, cb_fdf, c};
 	int status = emub_bfgs_set(bf, &fn, x_init + 1, o->step_size, o->tol); /* skip the amplitude, :665-668 */
@@ -212,6 +217,9 @@ static void *chain_main(void *arg)
 static int estimate_impl(emub_model *model, int ncomp, const double *ranges, const double *starts,
                          const emub_estimate_opts *opts_in, double *thetas_out, double *best_lhood,
                          emub_estimate_stats *stats);
+static int estimate_front(emub_model *model, int ncomp, const double *ranges, const double *starts, int starts_per_comp,
+                          const emub_estimate_opts *opts_in, double *thetas_out, double *best_lhood,
+                          emub_estimate_stats *stats);
 
 int emub_estimate_thetas(emub_model *model, const double *ranges, const emub_estimate_opts *opts_in,
                          double *thetas_out, double *best_lhood, emub_estimate_stats *stats)
@@ -233,10 +241,49 @@ int emub_estimate_thetas_multi(emub_model *model, int ncomp, const double *range
 	return estimate_impl(model, ncomp, ranges, NULL, opts_in, thetas_out, best_lhood, stats);
 }
 
-/* ncomp components x nchains chains each, all in one evaluation front */
+/* the restarts, then the optional refinement of every component's best point (one chain per component, one front) */
 static int estimate_impl(emub_model *model, int ncomp, const double *ranges, const double *starts,
                          const emub_estimate_opts *opts_in, double *thetas_out, double *best_lhood,
                          emub_estimate_stats *stats)
+{
+	emub_estimate_opts o;
+	if (opts_in) o = *opts_in; else emub_estimate_default_opts(&o);
+	const int nth = emub_model_nthetas(model);
+	double *best = (double *)malloc(sizeof(double) * (size_t)(ncomp > 0 ? ncomp : 1));
+	int rc = estimate_front(model, ncomp, ranges, starts, 0, &o, thetas_out, best, stats);
+	if ((rc == EMUB_OK || rc == EMUB_EDOM) && o.polish_steps > 0) {
+		emub_estimate_opts po = o;
+		po.max_tries = 1; po.nchains = 1; po.step_max = o.polish_steps; po.eps_abs = o.polish_eps;
+		double *th2 = (double *)malloc(sizeof(double) * (size_t)ncomp * nth);
+		double *best2 = (double *)malloc(sizeof(double) * (size_t)ncomp);
+		emub_estimate_stats st2;
+		/* the refinement follows the TRUE gradient of the objective (EMUB_GRAD_EXACT): the reference's formula is not the
+		 * gradient of what evalFnMulti returns, so its zero is not the likelihood's maximum.  A component without any
+		 * finite restart has nothing to refine: its start stays at zeros and is rejected again. */
+		const int prev_mode = emub_model_gradient_mode(model);
+		emub_model_set_gradient_mode(model, EMUB_GRAD_EXACT);
+		int rc2 = estimate_front(model, ncomp, ranges, thetas_out, 1, &po, th2, best2, &st2);
+		emub_model_set_gradient_mode(model, prev_mode);
+		if (rc2 == EMUB_OK || rc2 == EMUB_EDOM) {
+			for (int k = 0; k < ncomp; k++)
+				if (best[k] != SCREWUPVALUE && best2[k] != SCREWUPVALUE && best2[k] > best[k]) {
+					best[k] = best2[k];
+					memcpy(thetas_out + (size_t)k * nth, th2 + (size_t)k * nth, sizeof(double) * (size_t)nth);
+				}
+			if (stats) { stats->evaluations += st2.evaluations; stats->batches += st2.batches; }
+		} else
+			rc = rc2;
+		free(th2); free(best2);
+	}
+	if (best_lhood) memcpy(best_lhood, best, sizeof(double) * (size_t)ncomp);
+	free(best);
+	return rc;
+}
+
+/* ncomp components x nchains chains each, all in one evaluation front */
+static int estimate_front(emub_model *model, int ncomp, const double *ranges, const double *starts, int starts_per_comp,
+                          const emub_estimate_opts *opts_in, double *thetas_out, double *best_lhood,
+                          emub_estimate_stats *stats)
 {
 	if (!model || (!ranges && !starts) || !thetas_out) return EMUB_EINVAL;
 	emub_estimate_opts o;
@@ -247,7 +294,7 @@ static int estimate_impl(emub_model *model, int ncomp, const double *ranges, con
 	int nchains = per_comp * ncomp;
 	front_t fr;
 	memset(&fr, 0, sizeof(fr));
-	fr.model = model; fr.opts = &o; fr.ranges = ranges; fr.starts = starts;
+	fr.model = model; fr.opts = &o; fr.ranges = ranges; fr.starts = starts; fr.starts_per_comp = starts_per_comp;
 	fr.nth = emub_model_nthetas(model); fr.nth1 = fr.nth - 1; fr.nchains = nchains;
 	pthread_mutex_init(&fr.mu, NULL);
 	pthread_cond_init(&fr.cv_disp, NULL);
@@ -346,6 +393,7 @@ typedef struct {
 	const double *X, *Z;
 	int ldx, n, d, ldz, ncomp, kernel, order, max_slots;
 	emub_estimate_opts opts;
+	const double *ranges_in; /* NULL: emub_optimization_ranges of the design */
 	double *thetas_out, *best;
 	emub_estimate_stats stats;
 	int rc;
@@ -366,7 +414,8 @@ static void *dev_main(void *arg)
 	double *ranges = (double *)malloc(sizeof(double) * 2 * (size_t)nth);
 	double *th = (double *)calloc((size_t)nloc * nth, sizeof(double));
 	double *best = (double *)calloc((size_t)nloc, sizeof(double));
-	emub_optimization_ranges(j->kernel, j->X, j->ldx, j->n, j->d, ranges);
+	if (j->ranges_in) memcpy(ranges, j->ranges_in, sizeof(double) * 2 * (size_t)nth);
+	else emub_optimization_ranges(j->kernel, j->X, j->ldx, j->n, j->d, ranges);
 	j->rc = emub_ctx_create(j->device, &ctx);
 	if (j->rc == EMUB_OK) j->rc = emub_model_create(ctx, j->X, j->ldx, j->n, j->d, Y, j->kernel, j->order, j->max_slots, &m);
 	if (j->rc == EMUB_OK) j->rc = emub_model_set_training_multi(m, Y, nloc, nloc);
@@ -390,6 +439,15 @@ int emub_estimate_thetas_multi_devices(const int *devices, int ndev, const doubl
                                        int max_slots, const emub_estimate_opts *opts_in, double *thetas_out,
                                        double *best_lhood, emub_estimate_stats *stats)
 {
+	return emub_estimate_thetas_multi_devices_ranges(devices, ndev, X, ldx, n, d, Z, ldz, ncomp, kernel, regression_order, max_slots,
+	                                                 NULL, opts_in, thetas_out, best_lhood, stats);
+}
+
+int emub_estimate_thetas_multi_devices_ranges(const int *devices, int ndev, const double *X, int ldx, int n, int d,
+                                              const double *Z, int ldz, int ncomp, int kernel, int regression_order,
+                                              int max_slots, const double *ranges, const emub_estimate_opts *opts_in,
+                                              double *thetas_out, double *best_lhood, emub_estimate_stats *stats)
+{
 	if (!devices || ndev < 1 || ndev > 64 || !X || !Z || ncomp < 1 || !thetas_out || !best_lhood) return EMUB_EINVAL;
 	dev_job jobs[64];
 	pthread_t th[64];
@@ -400,7 +458,7 @@ int emub_estimate_thetas_multi_devices(const int *devices, int ndev, const doubl
 		memset(j, 0, sizeof(*j));
 		j->device = devices[g]; j->g = g; j->ndev = ndev; j->X = X; j->Z = Z; j->ldx = ldx; j->n = n; j->d = d; j->ldz = ldz;
 		j->ncomp = ncomp; j->kernel = kernel; j->order = regression_order; j->max_slots = max_slots; j->opts = o;
-		j->thetas_out = thetas_out; j->best = best_lhood;
+		j->thetas_out = thetas_out; j->best = best_lhood; j->ranges_in = ranges;
 		pthread_create(&th[g], NULL, dev_main, j);
 	}
 	int rc = EMUB_OK;

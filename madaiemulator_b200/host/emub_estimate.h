@@ -29,6 +29,13 @@ typedef struct {
 	/* start-point stream of local component k: seed + (first_component + k * component_stride) * 0x9E3779B97F4A7C15,
 	 * so that components keep their streams when they are sharded over devices (defaults 0 and 1) */
 	int first_component, component_stride;
+	/* Optional refinement, off by default (0): after the restarts, one more BFGS run per component from its best
+	 * point, on the TRUE gradient of the objective (EMUB_GRAD_EXACT, include/emu_b200.h), with the tighter gradient
+	 * tolerance polish_eps and at most polish_steps iterations; kept only if the likelihood improves.  The reference's
+	 * gradient formula is not the gradient of its own objective and its chains stop at |g| < 0.1, so where a restart
+	 * ends is partly chance; the extra run costs a handful of batched evaluations and can only raise the likelihood. */
+	int polish_steps;
+	double polish_eps;
 } emub_estimate_opts;
 
 typedef struct {
@@ -83,6 +90,13 @@ int emub_estimate_thetas_multi_devices(const int *devices, int ndev, const doubl
                                        const double *Z, int ldz, int ncomp, int kernel, int regression_order,
                                        int max_slots, const emub_estimate_opts *opts, double *thetas_out,
                                        double *best_lhood, emub_estimate_stats *stats);
+
+/* the same with explicit optimisation ranges (nthetas x 2, e.g. a reference optstruct's grad_ranges); NULL = the
+ * ranges emub_optimization_ranges derives from the design */
+int emub_estimate_thetas_multi_devices_ranges(const int *devices, int ndev, const double *X, int ldx, int n, int d,
+                                              const double *Z, int ldz, int ncomp, int kernel, int regression_order,
+                                              int max_slots, const double *ranges, const emub_estimate_opts *opts,
+                                              double *thetas_out, double *best_lhood, emub_estimate_stats *stats);
 
 #ifdef __cplusplus
 }

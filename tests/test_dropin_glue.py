@@ -134,3 +134,99 @@ def test_reference_cli_trains_on_the_engine(tmp_path):
         l_ours = -po.loglik_grad(th1[1:], want_grad=False)["negL"]
         l_ref = -po.loglik_grad(th0[1:], want_grad=False)["negL"]
         assert l_ours >= l_ref - 1e-3 * max(1.0, abs(l_ref)), (l_ours, l_ref)
+
+
+# ---- the multivariate front doors over the batched entry points (integration/multivar_glue.c) -------------
+def _multi_bin(name):
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", name)
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/%s not built" % name)
+    return root, path
+
+
+@pytest.mark.parametrize("flag,golden,nr", [(None, "multi-simple-o0.interactive.txt", None),
+                                            ("--pca_output", "multi-simple-o0.interactive_pca.txt", 5)])
+def test_reference_cli_interactive_mode_with_batched_front_doors(flag, golden, nr):
+    """The reference's unmodified interactive_emulator.c; alloc_multi_emulator / emulate_point_multi[_pca] are the
+    glue's: one engine model with all PCA components, one device pass (back-projection included) per point."""
+    import os
+    import subprocess
+    from tests.test_interactive_stream import _compare_protocol
+    root, cli = _multi_bin("interactive_emulator_dropin_multi")
+    cdir = os.path.join(root, "tests", "golden", "cli")
+    inp = open(os.path.join(cdir, "multi-simple.points"), "rb").read()
+    cmd = [cli, "interactive_mode", os.path.join(cdir, "multi-simple-o0.snapshot")] + ([flag] if flag else [])
+    out = subprocess.run(cmd, input=inp, capture_output=True, check=True, timeout=300).stdout.decode()
+    _compare_protocol(out, os.path.join(cdir, golden), 6, 0 if flag else 1 + 3 + 1 + 12, nr)
+
+
+def test_emuplusplus_with_batched_front_doors():
+    import os
+    import subprocess
+    root, dro_bin = _multi_bin("emuplusplus_dropin_multi")
+    ref_bin = os.path.join(root, "oracle", "_ref", "emuplusplus_ref")
+    if not os.path.exists(ref_bin):
+        pytest.skip("oracle/_ref/emuplusplus_ref not built")
+    snap = os.path.join(root, "tests", "golden", "cli", "multi-simple-o0.snapshot")
+    pts = "".join(open(os.path.join(root, "tests", "golden", "cli", "multi-simple.points")).readlines()[:25]).encode()
+    a = subprocess.run([ref_bin, snap], input=pts, capture_output=True, check=True, timeout=300).stdout.decode().split("\n")
+    b = subprocess.run([dro_bin, snap], input=pts, capture_output=True, check=True, timeout=300).stdout.decode().split("\n")
+    assert len(a) == len(b) and len(a) > 70
+    for la, lb in zip(a, b):
+        if la.startswith("# mean:") or la.startswith("# err:"):
+            va = np.array(la.split(":")[1].split(), dtype=np.float64)
+            vb = np.array(lb.split(":")[1].split(), dtype=np.float64)
+            assert np.allclose(va, vb, rtol=2e-6, atol=1e-9)
+        else:
+            assert la == lb
+
+
+def test_reference_cli_trains_all_components_in_one_front(tmp_path):
+    """BASELINE config 1 (multi-simple: 3 parameters, 6 outputs -> 5 PCA components) trained through the reference's
+    UNCHANGED CLI with estimate_multi bound to the batched driver: the restart chains of all 5 components share one
+    evaluation front.  Every component must reach a likelihood no worse than the reference's own CPU training."""
+    import ctypes
+    import os
+    import subprocess
+    from madaiemulator_b200 import engine
+    from oracle.pyoracle import PortOracle
+    from tests.test_interactive_stream import _Snap
+    root, cli = _multi_bin("interactive_emulator_dropin_multi")
+    H = engine.host_lib()
+    H.emub_snapshot_load_path.restype = ctypes.POINTER(_Snap)
+    H.emub_snapshot_load_path.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+
+    def components_of(path):
+        err = ctypes.create_string_buffer(256)
+        sp = H.emub_snapshot_load_path(path.encode(), err, 256)
+        assert sp, err.value
+        s = sp.contents
+        out = []
+        for c in range(s.nr):
+            comp = s.components[c]
+            n, d = comp.nmodel_points, comp.nparams
+            out.append((np.ctypeslib.as_array(comp.xmodel, (n * d,)).reshape(n, d).copy(),
+                        np.ctypeslib.as_array(comp.training_vector, (n,)).copy(),
+                        np.ctypeslib.as_array(comp.thetas, (comp.nthetas,)).copy(), comp.regression_order))
+        return out
+
+    ref_snap = os.path.join(root, "tests", "golden", "cli", "multi-simple-o0.snapshot")
+    tok = open(ref_snap).read().split()
+    nt, nr, d, n = int(tok[0]), int(tok[1]), int(tok[2]), int(tok[3])
+    inp = tmp_path / "multi-test-input.dat"
+    inp.write_text("%d\n%d\n%d\n" % (nt, d, n) + "\n".join(tok[6:6 + n * d]) + "\n" + "\n".join(tok[6 + n * d:6 + n * d + n * nt]) + "\n")
+    out_snap = tmp_path / "trained_on_gpu.snapshot"
+    env = dict(os.environ, EMUB_TRIES="400", EMUB_SLOTS="16", EMUB_SEED="7")
+    subprocess.run([cli, "estimate_thetas", str(inp), str(out_snap), "--regression_order=0"], check=True, timeout=900, env=env,
+                   stdout=subprocess.DEVNULL)
+    ours, ref = components_of(str(out_snap)), components_of(ref_snap)
+    assert len(ours) == len(ref) == nr == 5
+    for (X1, y1, th1, o1), (X0, y0, th0, o0) in zip(ours, ref):
+        # the PCA is the reference's own code in both runs: same components up to rounding
+        assert np.allclose(X1, X0) and np.allclose(y1, y0, atol=1e-9) and o1 == o0 == 0
+        po = PortOracle(X0, y0, 1, o0)
+        l_ours = -po.loglik_grad(th1[1:], want_grad=False)["negL"]
+        l_ref = -po.loglik_grad(th0[1:], want_grad=False)["negL"]
+        assert l_ours >= l_ref - 1e-3 * max(1.0, abs(l_ref)), (l_ours, l_ref)

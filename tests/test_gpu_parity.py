@@ -332,3 +332,39 @@ def test_cfg4_n8192_d15_properties(ctx):
     gk = -1.0 * (-0.5 * s2 * np.sum(Cinv * D) + 0.5 * s2 * (alpha @ D @ alpha))
     assert abs(r["grad"][0][1 + k] - gk) < 1e-8 * (abs(0.5 * s2 * np.sum(Cinv * D)) + abs(0.5 * s2 * (alpha @ D @ alpha)))
     m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,d,order,kernel", [(150, 3, 1, 1), (300, 6, 0, 1), (200, 2, 2, 2), (200, 4, 1, 3)])
+def test_exact_gradient_mode_is_the_derivative_of_the_objective(ctx, n, d, order, kernel):
+    """Deviation D-4 (optional mode): EMUB_GRAD_EXACT returns d(-L)/dtheta of the objective evalFnMulti returns --
+    checked against central differences of the ORACLE's -L; the default (literal gradFnMulti formula) is untouched and
+    is measurably not that derivative."""
+    from madaiemulator_b200 import engine
+    from oracle.pyoracle import PortOracle
+    X = ds.synthetic_design(n, d)
+    y = ds.synthetic_response(X)
+    m = engine.Model(ctx, X, y, kernel, order, max_slots=4)
+    o = PortOracle(X, y, kernel, order)
+    nth1 = m.nthetas - 1
+    rng = np.random.default_rng(5)
+    th = np.concatenate([[-3.0], rng.uniform(0.2, 1.0, nth1 - 1)]) if kernel == 1 else np.array([-3.0, 0.4])
+    lit = m.loglik_grad_batch(th[None, :])
+    m.set_gradient_mode(True)
+    ex = m.loglik_grad_batch(np.tile(th, (3, 1)))
+    m.set_gradient_mode(False)
+    lit2 = m.loglik_grad_batch(th[None, :])
+    assert np.array_equal(lit["grad"], lit2["grad"]) and lit["negL"][0] == ex["negL"][0]  # the mode only changes the gradient
+    assert np.array_equal(ex["grad"][0], ex["grad"][1]) and np.array_equal(ex["grad"][0], ex["grad"][2])
+    fd = np.zeros(nth1)
+    for k in range(nth1):
+        h = 1e-5
+        tp, tm = th.copy(), th.copy()
+        tp[k] += h
+        tm[k] -= h
+        fd[k] = (o.loglik_grad(tp, want_grad=False)["negL"] - o.loglik_grad(tm, want_grad=False)["negL"]) / (2 * h)
+    scale = np.maximum(np.abs(fd), 1e-3 * np.max(np.abs(fd)))
+    assert np.max(np.abs(ex["grad"][0] - fd) / scale) < 1e-5, (ex["grad"][0], fd)
+    if kernel == 1 and d > 1:
+        assert np.max(np.abs(lit["grad"][0] - fd) / scale) > 1e-3  # the literal formula is something else
+    m.close()
