@@ -72,6 +72,37 @@ def test_estimate_thetas_reaches_reference_likelihood(name, tries):
     ctx.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["uni-simple-o1", "multi-simple-pc0-o0"])
+def test_refinement_run_never_lowers_the_likelihood(name):
+    """The optional refinement (polish_steps > 0: one BFGS run from the best restart on the exact gradient) keeps the
+    restart result unless it finds a higher likelihood, ends at a stationary point of the objective, and does not
+    leave the model in exact-gradient mode."""
+    from madaiemulator_b200 import engine
+    from oracle.pyoracle import PortOracle
+    c = load_golden(name)
+    ctx = engine.Context(0)
+    m = engine.Model(ctx, c["X"], c["y"], c["kernel"], c["order"], max_slots=16)
+    th0, best0, st0 = engine.estimate_thetas(m, max_tries=8, nchains=8, seed=3)
+    th1, best1, st1 = engine.estimate_thetas(m, max_tries=8, nchains=8, seed=3, polish_steps=100)
+    assert best1 >= best0 and st1["evaluations"] > st0["evaluations"]
+    po = PortOracle(c["X"], c["y"], c["kernel"], c["order"])
+    assert abs(-po.loglik_grad(th1[1:], want_grad=False)["negL"] - best1) <= 1e-9 * max(1.0, abs(best1))
+    # stationary for the true gradient (|g| < polish_eps = 1e-3 unless the step budget ran out), not for the literal one
+    m.set_gradient_mode(True)
+    g = m.loglik_grad_batch(th1[None, 1:])["grad"][0]
+    m.set_gradient_mode(False)
+    if best1 > best0:
+        assert np.linalg.norm(g) < 0.05
+    # the default mode is back: same gradient as a fresh literal evaluation
+    lit = m.loglik_grad_batch(th1[None, 1:])["grad"][0]
+    ref = po.loglik_grad(th1[1:])["grad"]
+    scale = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))
+    assert np.max(np.abs(lit - ref) / scale) < 1e-6
+    m.close()
+    ctx.close()
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (CPU only: the reference's own evalFnGradMulti from oracle/_ref) prints one JSON
     line with the contract's keys."""
