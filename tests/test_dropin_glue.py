@@ -230,3 +230,31 @@ def test_reference_cli_trains_all_components_in_one_front(tmp_path):
         l_ours = -po.loglik_grad(th1[1:], want_grad=False)["negL"]
         l_ref = -po.loglik_grad(th0[1:], want_grad=False)["negL"]
         assert l_ours >= l_ref - 1e-3 * max(1.0, abs(l_ref)), (l_ours, l_ref)
+
+
+def test_batched_front_doors_shard_over_two_gpus(tmp_path):
+    """EMUB_DEVICES=0,1: estimate_multi sends component c to device c mod 2 (no exchange between devices) and
+    alloc_multi_emulator replicates the factors; same seed -> byte-identical snapshot and answers as on one GPU."""
+    import os
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root, cli = _multi_bin("interactive_emulator_dropin_multi")
+    cdir = os.path.join(root, "tests", "golden", "cli")
+    tok = open(os.path.join(cdir, "multi-simple-o0.snapshot")).read().split()
+    nt, d, n = int(tok[0]), int(tok[2]), int(tok[3])
+    inp = tmp_path / "multi-test-input.dat"
+    inp.write_text("%d\n%d\n%d\n" % (nt, d, n) + "\n".join(tok[6:6 + n * d]) + "\n" + "\n".join(tok[6 + n * d:6 + n * d + n * nt]) + "\n")
+    outs = []
+    for devs in ("0", "0,1"):
+        env = dict(os.environ, EMUB_TRIES="48", EMUB_SLOTS="16", EMUB_SEED="3", EMUB_DEVICES=devs)
+        snap = tmp_path / ("trained_%d.snapshot" % len(outs))
+        subprocess.run([cli, "estimate_thetas", str(inp), str(snap), "--regression_order=0"], check=True, timeout=900, env=env,
+                       stdout=subprocess.DEVNULL)
+        pts = open(os.path.join(cdir, "multi-simple.points"), "rb").read()
+        ans = subprocess.run([cli, "interactive_mode", str(snap), "--quiet"], input=pts, capture_output=True, check=True, timeout=300,
+                             env=env).stdout
+        outs.append((snap.read_bytes(), ans))
+    assert outs[0][0] == outs[1][0]
+    assert outs[0][1] == outs[1][1]
