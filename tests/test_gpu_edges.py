@@ -146,3 +146,37 @@ def test_argument_validation(ctx):
     assert m9.p == 1
     m9.close()
     m.close()
+
+
+def test_handles_release_their_device_memory(ctx):
+    """create / use / destroy in a loop (models, training-vector changes, emulators, query workspaces, captured graphs):
+    free device memory returns to where it was -- no handle leaks."""
+    import torch
+    from madaiemulator_b200 import engine
+    n, d = 700, 4
+    X = ds.synthetic_design(n, d)
+    y = ds.synthetic_response(X)
+    ths = np.tile(ds.default_theta_less_amp(d), (6, 1))
+    full = np.concatenate([[0.1], ths[0]])
+    pts = ds.synthetic_queries(300, d)
+
+    def cycle():
+        m = engine.Model(ctx, X, y, engine.POWEREXP, 1, max_slots=4)
+        m.loglik_grad_batch(ths)                      # graph capture for (4, ..) and (2, ..) chunks
+        m.set_training_multi(np.stack([y, 2 * y, y * y], axis=1))
+        m.loglik_grad_batch(ths, comp=np.array([0, 1, 2, 0, 1, 2], dtype=np.int32))
+        es = [m.emulator(full, comp=c) for c in range(3)]
+        engine.predict_multi(es, pts)
+        es[0].emulate(pts)
+        for e in es:
+            e.close()
+        m.close()
+
+    cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    for _ in range(5):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info(0)[0]
+    assert abs(free1 - free0) <= (8 << 20), (free0, free1)  # within the allocator's own granularity
