@@ -9,6 +9,7 @@
  *   evalFnMulti, gradFnMulti, evalFnGradMulti, estimateSigmaFull      src/libEmu/maxmultimin.c:288,416,615,148
  *   estimate_thetas_threaded                                         src/libEmu/estimate_threaded.c:78
  *   alloc_emulator_struct, free_emulator_struct, emulate_point       src/emulator_struct.c:13,43,124
+ *   emulateAtPointList, emulateAtPoint                               src/libEmu/emulate-fns.c:73,138
  *   makeCovMatrix_fnptr                                              src/libEmu/emulator.c:636
  *
  * Engine handles are kept in side tables keyed by the reference's struct pointers, so no reference
@@ -29,6 +30,7 @@
 #include "libEmu/emulator.h"
 #include "libEmu/maxmultimin.h"
 #include "libEmu/estimate_threaded.h"
+#include "libEmu/emulate-fns.h"
 
 #include "emu_b200.h"
 #include "emub_estimate.h"
@@ -37,9 +39,9 @@
 
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static emub_ctx *g_ctx = NULL;
-static struct { const void *key_x, *key_y; int n, d, kernel, order; emub_model *m; } g_models[GLUE_MAX];
+static struct { const void *key_x, *key_y; int n, d, kernel, order; unsigned long long hash; emub_model *m; } g_models[GLUE_MAX];
 static int g_nmodels = 0;
-static struct { const emulator_struct *key; emub_emulator *e; } g_emus[GLUE_MAX];
+static struct { const emulator_struct *key; emub_emulator *e; emub_model *m; } g_emus[GLUE_MAX];
 static int g_nemus = 0;
 
 static int env_int(const char *name, int dflt)
@@ -60,18 +62,46 @@ static emub_ctx *glue_ctx(void)
 	return g_ctx;
 }
 
+/* FNV-1a over the design and the training vector: a modelstruct is recognised by its buffers AND their contents, so a
+ * caller that frees a model and gets the same addresses back for another one (the R entry points build a model per
+ * call) never meets a stale engine copy */
+static unsigned long long glue_hash(modelstruct *ms)
+{
+	unsigned long long h = 1469598103934665603ull;
+	const int n = ms->options->nmodel_points, d = ms->options->nparams;
+	for (int i = 0; i < n; i++) {
+		for (int k = 0; k <= d; k++) {
+			const double v = k < d ? gsl_matrix_get(ms->xmodel, i, k) : gsl_vector_get(ms->training_vector, i);
+			unsigned long long bits;
+			memcpy(&bits, &v, sizeof(bits));
+			h = (h ^ bits) * 1099511628211ull;
+		}
+	}
+	return h;
+}
+
 /* the engine model that belongs to a reference modelstruct (created on first use) */
 static emub_model *glue_model_for(modelstruct *ms)
 {
 	optstruct *o = ms->options;
+	const unsigned long long hash = glue_hash(ms);
 	pthread_mutex_lock(&g_mu);
 	for (int i = 0; i < g_nmodels; i++)
 		if (g_models[i].key_x == ms->xmodel->data && g_models[i].key_y == ms->training_vector->data &&
 		    g_models[i].n == o->nmodel_points && g_models[i].d == o->nparams && g_models[i].kernel == o->cov_fn_index &&
 		    g_models[i].order == o->regression_order) {
-			emub_model *m = g_models[i].m;
-			pthread_mutex_unlock(&g_mu);
-			return m;
+			if (g_models[i].hash == hash) {
+				emub_model *m = g_models[i].m;
+				pthread_mutex_unlock(&g_mu);
+				return m;
+			}
+			/* same buffers, other contents: the old engine copy (and the emulators cached from it) is dead */
+			for (int k = 0; k < g_nemus;)
+				if (g_emus[k].m == g_models[i].m) { emub_emulator_destroy(g_emus[k].e); g_emus[k] = g_emus[--g_nemus]; }
+				else k++;
+			emub_model_destroy(g_models[i].m);
+			g_models[i] = g_models[--g_nmodels];
+			break;
 		}
 	if (g_nmodels == GLUE_MAX) { pthread_mutex_unlock(&g_mu); fprintf(stderr, "libemu_glue: too many models\n"); exit(EXIT_FAILURE); }
 	/* training_vector may be a strided view: gather it */
@@ -86,6 +116,7 @@ static emub_model *glue_model_for(modelstruct *ms)
 	g_models[g_nmodels].n = o->nmodel_points; g_models[g_nmodels].d = o->nparams;
 	g_models[g_nmodels].kernel = o->cov_fn_index; g_models[g_nmodels].order = o->regression_order;
 	g_models[g_nmodels].m = m;
+	g_models[g_nmodels].hash = hash;
 	g_nmodels++;
 	pthread_mutex_unlock(&g_mu);
 	return m;
@@ -205,7 +236,7 @@ emulator_struct *alloc_emulator_struct(modelstruct *model)
 	for (int i = 0; i < e->nregression_fns; i++) gsl_vector_set(e->beta_vector, i, beta[i]);
 	pthread_mutex_lock(&g_mu);
 	if (g_nemus == GLUE_MAX) { fprintf(stderr, "libemu_glue: too many emulators\n"); exit(EXIT_FAILURE); }
-	g_emus[g_nemus].key = e; g_emus[g_nemus].e = eh; g_nemus++;
+	g_emus[g_nemus].key = e; g_emus[g_nemus].e = eh; g_emus[g_nemus].m = m; g_nemus++;
 	pthread_mutex_unlock(&g_mu);
 	return e;
 }
@@ -240,6 +271,39 @@ void emulate_point(emulator_struct *e, gsl_vector *point, double *mean, double *
 	double x[64];
 	for (int i = 0; i < e->nparams; i++) x[i] = gsl_vector_get(point, i);
 	if (!eh || emub_predict_batch(eh, x, e->nparams, 1, mean, variance) != EMUB_OK) glue_die("emub_predict_batch");
+}
+
+/* emulate-fns.c:73 -- covariance, factorisation and regression once, then every point of the list: one emulator, one
+ * batched prediction (options->nemulate_points rows of point_list) */
+void emulateAtPointList(modelstruct *the_model, gsl_matrix *point_list, optstruct *options, double *the_mean, double *the_variance)
+{
+	emub_model *m = glue_model_for(the_model);
+	double th[64];
+	for (int i = 0; i < options->nthetas; i++) th[i] = gsl_vector_get(the_model->thetas, i);
+	emub_emulator *eh = NULL;
+	if (emub_emulator_create(m, th, &eh) != EMUB_OK) { /* chol_inverse_cov_matrix exits on a failed factorisation, :282-285 */
+		fprintf(stderr, "emulateAtPointList: %s\n", emub_last_error());
+		exit(EXIT_FAILURE);
+	}
+	if (emub_predict_batch(eh, point_list->data, (int)point_list->tda, options->nemulate_points, the_mean, the_variance) != EMUB_OK)
+		glue_die("emub_predict_batch");
+	emub_emulator_destroy(eh);
+}
+
+/* emulate-fns.c:138 */
+void emulateAtPoint(modelstruct *the_model, gsl_vector *the_point, optstruct *options, double *the_mean, double *the_variance)
+{
+	emub_model *m = glue_model_for(the_model);
+	double th[64], x[64];
+	for (int i = 0; i < options->nthetas; i++) th[i] = gsl_vector_get(the_model->thetas, i);
+	for (int i = 0; i < options->nparams; i++) x[i] = gsl_vector_get(the_point, i);
+	emub_emulator *eh = NULL;
+	if (emub_emulator_create(m, th, &eh) != EMUB_OK) {
+		fprintf(stderr, "emulateAtPoint: %s\n", emub_last_error());
+		exit(EXIT_FAILURE);
+	}
+	if (emub_predict_batch(eh, x, options->nparams, 1, the_mean, the_variance) != EMUB_OK) glue_die("emub_predict_batch");
+	emub_emulator_destroy(eh);
 }
 
 /* emulator.c:636 -- the kernel is identified by the function pointer the caller passes */

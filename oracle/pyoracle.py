@@ -200,6 +200,9 @@ class RefOracle:
             L.ref_emulator_create.argtypes = [_vp, _dp]
             L.ref_emulator_free.argtypes = [_vp]
             L.ref_emulate.argtypes = [_vp, _dp, _ci, _dp, _dp]
+            if hasattr(L, "ref_emulate_at_point_list"):
+                L.ref_emulate_at_point_list.argtypes = [_vp, _dp, _dp, _ci, _ci, _dp, _dp]
+                L.ref_emulate_at_point_list.restype = None
             L.ref_emulator_beta.argtypes = [_vp, _dp]
             L.ref_max_with_multimin.restype = ctypes.c_double
             L.ref_max_with_multimin.argtypes = [_vp, _ci, ctypes.c_ulong, _dp]
@@ -276,6 +279,14 @@ class RefOracle:
 
     def emulator(self, thetas):
         return _RefEmulator(self, thetas)
+
+    def emulate_at_point_list(self, thetas, pts, single=False):
+        """emulateAtPointList (emulate-fns.c:73); single=True: emulateAtPoint (:138) point by point"""
+        pts = _c(pts).reshape(-1, self.d)
+        m = pts.shape[0]
+        mean, var = np.empty(m), np.empty(m)
+        self.L.ref_emulate_at_point_list(self.h, _P(_c(thetas)), _P(pts), m, 1 if single else 0, _P(mean), _P(var))
+        return mean, var
 
     def max_with_multimin(self, max_tries, seed):
         th = np.empty(self.nthetas)

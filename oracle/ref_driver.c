@@ -273,6 +273,29 @@ void ref_emulate(void *e, const double *pts, int m, double *mean, double *var)
 		emulate_point(es, &pv.vector, &mean[i], &var[i]);
 	}
 }
+/* -> emulateAtPointList, src/libEmu/emulate-fns.c:73 (the R binding's list entry point, rbind.c:178) and, with
+ * single != 0, emulateAtPoint (:138) point by point; thetas is the FULL vector, pts m x nparams row-major */
+void ref_emulate_at_point_list(void *h, const double *thetas, const double *pts, int m, int single, double *mean, double *var)
+{
+	ref_model *r = (ref_model *)h;
+	optstruct *o = r->model->options;
+	for (int i = 0; i < o->nthetas; i++) gsl_vector_set(r->model->thetas, i, thetas[i]);
+	const int saved = o->nemulate_points;
+	int so = silence_stdout();
+	if (single) {
+		for (int i = 0; i < m; i++) {
+			gsl_vector_view pv = gsl_vector_view_array((double *)pts + (size_t)i * o->nparams, o->nparams);
+			emulateAtPoint(r->model, &pv.vector, o, &mean[i], &var[i]);
+		}
+	} else {
+		o->nemulate_points = m;
+		gsl_matrix_view pl = gsl_matrix_view_array((double *)pts, m, o->nparams);
+		emulateAtPointList(r->model, &pl.matrix, o, mean, var);
+		o->nemulate_points = saved;
+	}
+	restore_stdout(so);
+}
+
 void ref_emulator_beta(void *e, double *beta_out)
 {
 	emulator_struct *es = (emulator_struct *)e;

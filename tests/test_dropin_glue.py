@@ -46,6 +46,39 @@ def test_reference_symbols_run_on_the_engine(oracles, name):
     del e
 
 
+@pytest.mark.parametrize("name", ["uni-simple-o1", "multi-simple-pc0-o1"])
+def test_point_list_entry_points_run_on_the_engine(oracles, name):
+    """emulateAtPointList / emulateAtPoint (emulate-fns.c:73,138; the R binding's callEmulateAtList / callEmulateAtPt):
+    the glue builds ONE emulator and answers the whole list with one batched prediction."""
+    po = oracles
+    c = load_golden(name)
+    ref = po.RefOracle(c["X"], c["y"], c["kernel"], c["order"])
+    dro = po.DropinOracle(c["X"], c["y"], c["kernel"], c["order"])
+    pts = c["pts"][:60]
+    m1, v1 = ref.emulate_at_point_list(c["theta_full"], pts)
+    m2, v2 = dro.emulate_at_point_list(c["theta_full"], pts)
+    assert relerr(m2, m1, 1e-3) < 1e-9
+    assert np.max(np.abs(v2 - v1)) < 1e-9 * max(1.0, float(c["kappa"]))
+    m3, v3 = dro.emulate_at_point_list(c["theta_full"], pts[:5], single=True)
+    assert np.array_equal(m3, m2[:5]) and np.array_equal(v3, v2[:5])
+
+
+def test_glue_recognises_a_model_by_its_contents(oracles):
+    """Two models that live at the same addresses one after the other (what the R entry points do: a modelstruct per
+    call) must not share an engine copy."""
+    po = oracles
+    c = load_golden("uni-simple-o1")
+    th = c["theta_less_amp"]
+    vals = []
+    for scale in (1.0, 3.0, 1.0):
+        dro = po.DropinOracle(c["X"], scale * c["y"], c["kernel"], c["order"])
+        ref = po.RefOracle(c["X"], scale * c["y"], c["kernel"], c["order"])
+        assert relerr(dro.sigma_full(th), ref.sigma_full(th)) < 1e-9
+        vals.append(dro.sigma_full(th))
+        del dro, ref
+    assert relerr(vals[1], 9.0 * vals[0]) < 1e-9 and vals[2] == vals[0]
+
+
 def test_reference_restart_driver_on_the_engine(oracles):
     """The reference's unmodified maxWithMultiMin / doOptimizeMultiMin, every likelihood call served by the GPU:
     same seed, same start points -> the same optimum as the all-CPU reference."""
