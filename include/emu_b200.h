@@ -116,7 +116,7 @@ int emub_emulator_beta(emub_emulator *e, double *beta); /* p values */
 int emub_predict_batch(emub_emulator *e, const double *pts, int ldp, int mq, double *mean, double *var);
 /* emulate_point_multi (multivar_support.c:103-157) for mq points: all nr PCA components (emulators of one model) and
  * the back-projection  mean_i = ybar_i + sum_j U_ij sqrt(lambda_j) m_j,  var_i = sum_j U_ij^2 lambda_j v_j  on the
- * device; evecs is nt x nr row-major.  mean, var: mq x nt.  nt = 0: PCA-space output mq x nr
+ * device; evecs is nt x nr row-major.  mean, var: mq x nt (nt, nr <= 1024).  nt = 0: PCA-space output mq x nr
  * (emulate_point_multi_pca, multivar_support.c:78) */
 int emub_predict_multi(emub_emulator *const *emus, int nr, const double *pts, int ldp, int mq, int nt,
                        const double *training_mean, const double *evecs, const double *evals, double *mean, double *var);

@@ -121,6 +121,7 @@ struct emub_model {
 // query workspace: one chunk of up to mqc points
 struct QueryWs {
 	int mqc;      // query chunk (multiple of 128)
+	int ntcap;    // observables the output / projection buffers hold (grown on demand, ensure_output_capacity)
 	int ncomp;    // rows of dMean / dVar
 	double *dQ, *dK, *dVsq, *dKA, *dMean, *dVar;  // dMean, dVar: ncomp x mqc
 	double *dOutM, *dOutV, *dProj;                // back-projected outputs (mqc x ntmax), projection data
@@ -131,7 +132,8 @@ struct QueryWs {
 	cudaStream_t copy_stream;
 	cudaEvent_t evIn[2], evOut[2];
 };
-constexpr int NTMAX = 64;  // observables per multivariate model supported by the fused back-projection
+constexpr int NTMAX = 64;     // observables (or components) the back-projection buffers start out with
+constexpr int NTLIMIT = 1024; // ... and the most they grow to
 
 struct emub_emulator {
 	emub_model *m;
@@ -901,6 +903,7 @@ static int ensure_query_ws(emub_model *m)
 	CUDA_TRY(cudaMalloc(&w->dKA, sizeof(double) * (size_t)mqc * m->ncp));
 	CUDA_TRY(cudaMalloc(&w->dMean, sizeof(double) * (size_t)w->ncomp * mqc));
 	CUDA_TRY(cudaMalloc(&w->dVar, sizeof(double) * (size_t)w->ncomp * mqc));
+	w->ntcap = NTMAX;
 	CUDA_TRY(cudaMalloc(&w->dOutM, sizeof(double) * (size_t)NTMAX * mqc));
 	CUDA_TRY(cudaMalloc(&w->dOutV, sizeof(double) * (size_t)NTMAX * mqc));
 	CUDA_TRY(cudaMalloc(&w->dProj, sizeof(double) * (size_t)(NTMAX + NTMAX * NTMAX + NTMAX)));
@@ -920,6 +923,29 @@ static int ensure_query_ws(emub_model *m)
 	for (int i = m->nblk - 1; i >= 0; i--) tasks.push_back({(long long)i * TB * m->npad, 0, 0, (i + 1) * TB, i | TASK_TRIM_END_SR0});
 	CUDA_TRY(cudaMalloc(&w->dTasks, tasks.size() * sizeof(GemmTask)));
 	CUDA_TRY(cudaMemcpy(w->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
+	return EMUB_OK;
+}
+
+// back-projected outputs of a chunk are mqc x nt on the device and twice that in each pinned host buffer: grow them
+// when a model has more observables (or components) than the buffers were sized for
+static int ensure_output_capacity(emub_model *m, int need)
+{
+	QueryWs *w = m->qws;
+	if (need <= w->ntcap) return EMUB_OK;
+	const int cap = (need + 63) / 64 * 64;
+	CUDA_TRY(cudaStreamSynchronize(m->ctx->streams[0]));
+	cudaFree(w->dOutM); cudaFree(w->dOutV); cudaFree(w->dProj);
+	cudaFreeHost(w->hOutb[0]); cudaFreeHost(w->hOutb[1]);
+	w->dOutM = w->dOutV = w->dProj = nullptr;
+	w->hOut = w->hOutb[0] = w->hOutb[1] = nullptr;
+	w->ntcap = 0;
+	CUDA_TRY(cudaMalloc(&w->dOutM, sizeof(double) * (size_t)cap * w->mqc));
+	CUDA_TRY(cudaMalloc(&w->dOutV, sizeof(double) * (size_t)cap * w->mqc));
+	CUDA_TRY(cudaMalloc(&w->dProj, sizeof(double) * ((size_t)cap + (size_t)cap * cap + cap)));
+	CUDA_TRY(cudaMallocHost(&w->hOutb[0], sizeof(double) * 2 * (size_t)cap * w->mqc));
+	CUDA_TRY(cudaMallocHost(&w->hOutb[1], sizeof(double) * 2 * (size_t)cap * w->mqc));
+	w->hOut = w->hOutb[0];
+	w->ntcap = cap;
 	return EMUB_OK;
 }
 
@@ -1114,12 +1140,13 @@ extern "C" int emub_predict_multi(emub_emulator *const *emus, int nr, const doub
 	emub_model *m = emus[0]->m;
 	for (int j = 0; j < nr; j++)
 		if (!emus[j] || emus[j]->m != m) return set_err(EMUB_EINVAL, "emub_predict_multi: emulators must share one model%s");
-	if (nt > NTMAX || nr > NTMAX || (nt > 0 && (!training_mean || !evecs || !evals)) || ldp < m->d)
-		return set_err(EMUB_EINVAL, "emub_predict_multi: bad projection arguments%s");
+	if (nt > NTLIMIT || nr > NTLIMIT || (nt > 0 && (!training_mean || !evecs || !evals)) || ldp < m->d)
+		return set_err(EMUB_EINVAL, "emub_predict_multi: bad projection arguments (at most 1024 observables / components)%s");
 	CUDA_TRY(cudaSetDevice(m->ctx->device));
 	{ int rc0 = ensure_query_ws(m); if (rc0) return rc0; }
 	QueryWs *w = m->qws;
 	if (nr > w->ncomp) return set_err(EMUB_EINVAL, "emub_predict_multi: more emulators than model components%s");
+	{ int rc1 = ensure_output_capacity(m, std::max(nt, nr)); if (rc1) return rc1; }
 	cudaStream_t st = m->ctx->streams[0];
 	if (nt > 0) {
 		// projection data: ybar[nt] | evecs[nt x nr] | evals[nr]
@@ -1129,7 +1156,7 @@ extern "C" int emub_predict_multi(emub_emulator *const *emus, int nr, const doub
 		memcpy(proj.data() + nt + (size_t)nt * nr, evals, sizeof(double) * nr);
 		CUDA_TRY(cudaMemcpy(w->dProj, proj.data(), sizeof(double) * proj.size(), cudaMemcpyHostToDevice));
 	}
-	const size_t vofs = (size_t)NTMAX * w->mqc;  // variances start here in a host output buffer
+	const size_t vofs = (size_t)w->ntcap * w->mqc;  // variances start here in a host output buffer
 	return walk_query_chunks(
 	    m, pts, ldp, mq,
 	    [&](int cnt, const double *dQ, double *hOut) -> int {

@@ -88,6 +88,36 @@ def test_predict_multi_matches_oracle_backprojection(ctx):
     m.close()
 
 
+def test_predict_multi_many_observables(ctx):
+    """more observables than the back-projection buffers start out with (64): they grow on demand; the projection of
+    3 components onto 200 observables equals the host formula, and a later narrow call still works"""
+    from madaiemulator_b200 import engine
+    n, d, nr, nt = 200, 3, 3, 200
+    X = ds.synthetic_design(n, d)
+    rng = np.random.default_rng(4)
+    Z = rng.normal(size=(n, nr))
+    m = engine.Model(ctx, X, Z[:, 0], 1, 0, max_slots=2)
+    m.set_training_multi(Z)
+    thetas = np.stack([np.concatenate([[0.0, -3.0], rng.uniform(0.3, 1.0, d)]) for _ in range(nr)])
+    emus = [m.emulator(thetas[c], comp=c) for c in range(nr)]
+    pts = ds.synthetic_queries(500, d)
+    ybar, U, lam = rng.normal(size=nt), rng.normal(size=(nt, nr)), rng.uniform(0.5, 2.0, nr)
+    mp, vp = engine.predict_multi(emus, pts)
+    mean, var = engine.predict_multi(emus, pts, ybar, U, lam)
+    assert mean.shape == (500, nt)
+    em = ybar[None, :] + (mp * np.sqrt(lam)[None, :]) @ U.T
+    ev = (vp * lam[None, :]) @ (U * U).T
+    assert np.max(np.abs(mean - em)) < 1e-12 * max(1.0, np.max(np.abs(em)))
+    assert np.max(np.abs(var - ev)) < 1e-12 * max(1.0, np.max(np.abs(ev)))
+    mp2, vp2 = engine.predict_multi(emus, pts)
+    assert np.array_equal(mp, mp2) and np.array_equal(vp, vp2)
+    with pytest.raises(engine.EmubError):
+        engine.predict_multi(emus, pts, np.zeros(2000), np.zeros((2000, nr)), lam)
+    for e in emus:
+        e.close()
+    m.close()
+
+
 def test_estimate_multi_merges_fronts(ctx):
     """All components' restart chains in one evaluation front; component k's result equals a single-component run."""
     from madaiemulator_b200 import engine
