@@ -422,7 +422,13 @@ int emub_interactive_stream(emub_multi_emulator *me, FILE *in, FILE *out, int qu
 {
 	if (!me || !in || !out) return EMUB_EINVAL;
 	const int d = me->d, nt = me->nt;
-	if (block_points <= 0) block_points = 4 * 16384 * (me->nreplicas > 1 ? me->nreplicas : 1);
+	if (block_points <= 0) {
+		/* four device chunks per GPU, fewer when the model has so many observables that the answer blocks get large */
+		long per_dev = (4L << 20) / (nt > 0 ? nt : 1);
+		if (per_dev > 4 * 16384) per_dev = 4 * 16384;
+		if (per_dev < 16384) per_dev = 16384;
+		block_points = (int)per_dev * (me->nreplicas > 1 ? me->nreplicas : 1);
+	}
 	if (!quiet) { /* interactive_emulator.c:398-414 */
 		fprintf(out, "%d\n", d);
 		for (int i = 0; i < d; i++) fprintf(out, "%s%d\n", "param_", i);

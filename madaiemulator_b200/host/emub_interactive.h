@@ -40,7 +40,7 @@ size_t emub_parse_doubles(char *buf, size_t len, double *out, size_t max, int th
 
 /* the interactive_mode loop: reader / device / writer stages on their own host threads over a ring of blocks, text
  * conversion and "%.17f" formatting spread over EMUB_IO_THREADS (default: online cores - 2) worker threads.
- * block_points <= 0 selects 65536 per device.  Returns EMUB_OK at end of input; *npoints (optional)
+ * block_points <= 0 selects 65536 per device (fewer, down to 16384, for models with hundreds of observables).  Returns EMUB_OK at end of input; *npoints (optional)
  * = points answered.  binary != 0 selects the BINARY_INTERACTIVE_MODE framing (raw doubles in and out, :119). */
 int emub_interactive_stream(emub_multi_emulator *me, FILE *in, FILE *out, int quiet, int pca_output, int binary,
                             int block_points, long long *npoints);
