@@ -366,7 +366,11 @@ static void *device_stage(void *arg)
 			t0 = now_s();
 			const int rc = emub_multi_emulator_predict(sp->me, s->pts, s->m, sp->pca_output, s->mean, s->var);
 			sp->t_predict += now_s() - t0;
-			if (rc != EMUB_OK) { pthread_mutex_lock(&sp->mu); sp->rc = rc; pthread_mutex_unlock(&sp->mu); }
+			if (rc != EMUB_OK) {
+				/* the library's message is per thread: report it from the thread that has it */
+				fprintf(stderr, "emub_interactive_stream: prediction failed: %s\n", emub_last_error());
+				pthread_mutex_lock(&sp->mu); sp->rc = rc; pthread_mutex_unlock(&sp->mu);
+			}
 		}
 		const int last = s->last;
 		slot_set(sp, s, SLOT_PREDICTED);
