@@ -68,6 +68,7 @@ struct emub_ctx {
 	long long launches;
 	cudaEvent_t ev0, ev1;
 	cudaEvent_t gev[4];
+	long long small_launch_ctas;  // products with at most this many 64 x 64 sub-tiles run with 32 x 32 ones (EMUB_SMALL_CTAS)
 };
 
 // launch bookkeeping: in profile mode every launch is timed on its own (events + sync)
@@ -161,6 +162,8 @@ extern "C" int emub_ctx_create(int device, emub_ctx **out)
 	c->device = device;
 	c->ngroups = 2;
 	c->use_graphs = getenv("EMUB_NO_GRAPHS") ? 0 : 1;
+	// half of what the default configuration keeps resident (148 SMs x 4 CTAs)
+	c->small_launch_ctas = getenv("EMUB_SMALL_CTAS") ? atoll(getenv("EMUB_SMALL_CTAS")) : 296;
 	for (int g = 0; g < 4; g++) {
 		CUDA_TRY(cudaStreamCreateWithFlags(&c->streams[g], cudaStreamNonBlocking));
 		CUDA_TRY(cudaEventCreateWithFlags(&c->gev[g], cudaEventDisableTiming));
@@ -463,7 +466,11 @@ static void launch_gemm(emub_ctx *c, int fam, double flops, cudaStream_t st, con
 	if (ntasks <= 0 || batch <= 0) return;
 	GemmArgs a{tasks, A, B, C, sA, sB, sC, lda, ldb, ldc, alpha};
 	LaunchScope ls(c, fam, flops * batch, st);
-	k_gemm<AL, BL, EPI><<<dim3(ntasks * DefaultCfg::SUBS, batch), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(a);
+	// the column-sum epilogue lays its output out by sub-tile row, so it keeps the default configuration
+	if (EPI != EPI_COLSUMSQ && (long long)ntasks * DefaultCfg::SUBS * batch <= c->small_launch_ctas)
+		k_gemm<AL, BL, EPI, SmallCfg><<<dim3(ntasks * SmallCfg::SUBS, batch), SmallCfg::THREADS, SmallCfg::SMEM_BYTES, st>>>(a);
+	else
+		k_gemm<AL, BL, EPI><<<dim3(ntasks * DefaultCfg::SUBS, batch), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(a);
 }
 
 static void launch_cov(emub_model *m, cudaStream_t st, int count, const double *consts, double *out, long long ostride,

@@ -40,6 +40,11 @@ struct GemmCfg {
 	static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
 };
 using DefaultCfg = GemmCfg<64, 64, 2, 2, 8, 4, 4>;  // 4 CTAs / SM: 35.3 TFLOP/s on 4096^3 (cuBLAS: 35.2)
+// Launches that would not even half fill the GPU with 64 x 64 sub-tiles (the deep levels of the recursion when few
+// matrices are in flight) use 32 x 32 sub-tiles instead: 4x the CTAs, each with a quarter of the DMMAs per k-step.
+// Every output element still sees the same k-ordered sequence of DMMAs, so results do not depend on the choice (the
+// K-range trimming of the default configuration only skips products with structural zeros).
+using SmallCfg = GemmCfg<32, 32, 2, 2, 8, 4, 8>;
 constexpr int GEMM_THREADS = DefaultCfg::THREADS;
 constexpr int GEMM_SMEM_BYTES = DefaultCfg::SMEM_BYTES;
 
