@@ -114,12 +114,20 @@ void emub_emulator_destroy(emub_emulator *e);
 int emub_emulator_beta(emub_emulator *e, double *beta); /* p values */
 /* emulate_point (emulator_struct.c:124) for mq points: pts (mq x d, row stride ldp) -> mean[mq], var[mq] */
 int emub_predict_batch(emub_emulator *e, const double *pts, int ldp, int mq, double *mean, double *var);
+/* emulate_point for a handful of points (mq <= 8) -- the call pattern of an MCMC driver (EmuPlusPlus::QueryEmulator,
+ * EmuPlusPlus.cpp:137-179): a latency path that streams the cached factor once instead of running the batched tensor
+ * pass on a 128-column block (n = 4096: 340 -> about 100 us per call).  Same quantities as emub_predict_batch; the
+ * sums run in another order, so the two agree to rounding (1e-15), not bit for bit. */
+int emub_predict_few(emub_emulator *e, const double *pts, int ldp, int mq, double *mean, double *var);
 /* emulate_point_multi (multivar_support.c:103-157) for mq points: all nr PCA components (emulators of one model) and
  * the back-projection  mean_i = ybar_i + sum_j U_ij sqrt(lambda_j) m_j,  var_i = sum_j U_ij^2 lambda_j v_j  on the
  * device; evecs is nt x nr row-major.  mean, var: mq x nt (nt, nr <= 1024).  nt = 0: PCA-space output mq x nr
  * (emulate_point_multi_pca, multivar_support.c:78) */
 int emub_predict_multi(emub_emulator *const *emus, int nr, const double *pts, int ldp, int mq, int nt,
                        const double *training_mean, const double *evecs, const double *evals, double *mean, double *var);
+/* emub_predict_multi for a handful of points (mq <= 8) on the latency path (see emub_predict_few) */
+int emub_predict_multi_few(emub_emulator *const *emus, int nr, const double *pts, int ldp, int mq, int nt,
+                           const double *training_mean, const double *evecs, const double *evals, double *mean, double *var);
 /* device-pointer variant: d_pts is mq x d contiguous; asynchronous */
 int emub_predict_batch_dev(emub_emulator *e, const double *d_pts, int mq, double *d_mean, double *d_var);
 

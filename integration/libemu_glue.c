@@ -270,7 +270,7 @@ void emulate_point(emulator_struct *e, gsl_vector *point, double *mean, double *
 	emub_emulator *eh = glue_emulator_for(e, 0);
 	double x[64];
 	for (int i = 0; i < e->nparams; i++) x[i] = gsl_vector_get(point, i);
-	if (!eh || emub_predict_batch(eh, x, e->nparams, 1, mean, variance) != EMUB_OK) glue_die("emub_predict_batch");
+	if (!eh || emub_predict_few(eh, x, e->nparams, 1, mean, variance) != EMUB_OK) glue_die("emub_predict_few");
 }
 
 /* emulate-fns.c:73 -- covariance, factorisation and regression once, then every point of the list: one emulator, one
@@ -302,7 +302,7 @@ void emulateAtPoint(modelstruct *the_model, gsl_vector *the_point, optstruct *op
 		fprintf(stderr, "emulateAtPoint: %s\n", emub_last_error());
 		exit(EXIT_FAILURE);
 	}
-	if (emub_predict_batch(eh, x, options->nparams, 1, the_mean, the_variance) != EMUB_OK) glue_die("emub_predict_batch");
+	if (emub_predict_few(eh, x, options->nparams, 1, the_mean, the_variance) != EMUB_OK) glue_die("emub_predict_few");
 	emub_emulator_destroy(eh);
 }
 

@@ -10,7 +10,8 @@
  *                             -> one engine model carrying the nr training vectors + one cached factor per component,
  *                                replicated on every device of EMUB_DEVICES
  *   emulate_point_multi[_pca] multivar_support.c:78,103   nr emulate_point calls + back-projection on the host
- *                             -> one emub_predict_multi call: all components and the back-projection on the device
+ *                             -> one emub_predict_multi_few call (the latency path for single points): all components
+ *                                and the back-projection on the device
  *   free_multi_emulator       multivar_support.c:57
  *
  * Environment: EMUB_DEVICES ("0,1,..", default EMUB_DEVICE or 0), EMUB_TRIES (restarts per component, default
@@ -216,7 +217,7 @@ static void mv_emulate(multi_emulator *emu, gsl_vector *the_point, gsl_vector *t
 	const int d = emu->nparams, nt = emu->nt, nout = pca ? emu->nr : emu->nt;
 	if (d > 64 || nt > 4096) { fprintf(stderr, "multivar_glue: model too wide\n"); exit(EXIT_FAILURE); }
 	for (int k = 0; k < d; k++) pt[k] = gsl_vector_get(the_point, k);
-	if (emub_multi_emulator_predict(me, pt, 1, pca, mean, var) != EMUB_OK) mv_die("emulate_point_multi");
+	if (emub_multi_emulator_predict_few(me, pt, 1, pca, mean, var) != EMUB_OK) mv_die("emulate_point_multi");
 	for (int i = 0; i < nout; i++) {
 		gsl_vector_set(the_mean, i, mean[i]);
 		gsl_vector_set(the_variance, i, var[i]);

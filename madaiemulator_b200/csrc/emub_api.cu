@@ -125,6 +125,7 @@ struct QueryWs {
 	int ntcap;    // observables the output / projection buffers hold (grown on demand, ensure_output_capacity)
 	int ncomp;    // rows of dMean / dVar
 	double *dQ, *dK, *dVsq, *dKA, *dMean, *dVar;  // dMean, dVar: ncomp x mqc
+	double *dFew;                                 // partial products of the few-points path: [ceil(npad/FEW_JC)][npad][8]
 	double *dOutM, *dOutV, *dProj;                // back-projected outputs (mqc x ntmax), projection data
 	GemmTask *dTasks;
 	double *hQ, *hOut;  // pinned
@@ -400,7 +401,7 @@ static void free_query_ws(emub_model *m)
 	QueryWs *w = m->qws;
 	if (!w) return;
 	cudaFree(w->dQ); cudaFree(w->dK); cudaFree(w->dVsq); cudaFree(w->dKA); cudaFree(w->dMean); cudaFree(w->dVar);
-	cudaFree(w->dOutM); cudaFree(w->dOutV); cudaFree(w->dProj); cudaFree(w->dTasks);
+	cudaFree(w->dOutM); cudaFree(w->dOutV); cudaFree(w->dProj); cudaFree(w->dTasks); cudaFree(w->dFew);
 	cudaFreeHost(w->hQ); cudaFreeHost(w->hOut);
 	cudaFree(w->dQb[1]); cudaFreeHost(w->hQb[1]); cudaFreeHost(w->hOutb[1]);
 	if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
@@ -910,6 +911,7 @@ static int ensure_query_ws(emub_model *m)
 	CUDA_TRY(cudaMalloc(&w->dKA, sizeof(double) * (size_t)mqc * m->ncp));
 	CUDA_TRY(cudaMalloc(&w->dMean, sizeof(double) * (size_t)w->ncomp * mqc));
 	CUDA_TRY(cudaMalloc(&w->dVar, sizeof(double) * (size_t)w->ncomp * mqc));
+	CUDA_TRY(cudaMalloc(&w->dFew, sizeof(double) * (size_t)((m->npad + FEW_JC - 1) / FEW_JC) * m->npad * 8));
 	w->ntcap = NTMAX;
 	CUDA_TRY(cudaMalloc(&w->dOutM, sizeof(double) * (size_t)NTMAX * mqc));
 	CUDA_TRY(cudaMalloc(&w->dOutV, sizeof(double) * (size_t)NTMAX * mqc));
@@ -1027,7 +1029,7 @@ extern "C" int emub_emulator_beta(emub_emulator *e, double *beta)
 }
 
 // one chunk (mq <= mqc) whose points are already at dQ (contiguous mq x d)
-static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, int mq, double *dMean, double *dVar)
+static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, int mq, double *dMean, double *dVar, bool few = false)
 {
 	emub_model *m = e->m;
 	emub_ctx *c = m->ctx;
@@ -1035,6 +1037,24 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 	const int mq_pad = (mq + TB - 1) / TB * TB;
 	const int ldk = w->mqc;
 	launch_kcross(m, st, e->consts, dQ, mq, mq_pad, w->dK, ldk);
+	if (few && mq <= FEW_MAX && FEW_MAX * (m->npad / FEW_ROWS) <= w->mqc) {
+		// latency path: W K[:, 0:8] as a row- and column-split skinny product, one CTA for the reductions
+		{
+			LaunchScope ls(c, EMUB_K_GEMM_PRED, (double)m->npad * m->npad * 8, st);
+			k_few_wk<<<dim3(m->npad / 32, (m->npad + FEW_JC - 1) / FEW_JC), 256, 0, st>>>(e->W, m->npad, w->dK, ldk, w->dFew, m->npad);
+		}
+		{
+			LaunchScope ls(c, EMUB_K_SKINNY, 8.0 * (double)m->npad * (8 + m->ncp), st);
+			k_few_finish<<<m->npad / FEW_ROWS, FEW_ROWS, 0, st>>>(w->dFew, m->npad, w->dK, ldk, e->AB, m->ncp, w->dVsq, ldk, w->dKA);
+		}
+		{
+			LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);
+			k_pred_final<<<1, 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, m->npad / FEW_ROWS, ldk, e->beta, e->Minv,
+			                                e->kappa, dMean, dVar, m->npad / FEW_ROWS, (long long)FEW_MAX * m->ncp);
+		}
+		CUDA_TRY(cudaGetLastError());
+		return EMUB_OK;
+	}
 	const int nqb = mq_pad / TB;
 	// |W k|^2 partials: tile (row block i, query block qb)
 	launch_gemm<KMAJOR, RMAJOR, EPI_COLSUMSQ>(c, EMUB_K_GEMM_PRED, (double)m->npad * (m->npad + TB / 4) * TB, st, w->dTasks, m->nblk, nqb,
@@ -1047,7 +1067,7 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 	{
 		LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);
 		k_pred_final<<<(mq + 127) / 128, 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, m->nblk * DefaultCfg::SUBM, ldk, e->beta,
-		                                               e->Minv, e->kappa, dMean, dVar);
+		                                               e->Minv, e->kappa, dMean, dVar, 1, 0);
 	}
 	CUDA_TRY(cudaGetLastError());
 	return EMUB_OK;
@@ -1135,13 +1155,57 @@ extern "C" int emub_predict_batch(emub_emulator *e, const double *pts, int ldp, 
 	    });
 }
 
+// emulate_point for a handful of points (mq <= 8), the call pattern of an MCMC driver: no chunk walk, the skinny
+// latency path of predict_chunk
+extern "C" int emub_predict_few(emub_emulator *e, const double *pts, int ldp, int mq, double *mean, double *var)
+{
+	if (!e || !pts || !mean || !var || mq < 0 || mq > FEW_MAX || ldp < e->m->d) return set_err(EMUB_EINVAL, "emub_predict_few: bad argument (at most 8 points)%s");
+	if (mq == 0) return EMUB_OK;
+	emub_model *m = e->m;
+	CUDA_TRY(cudaSetDevice(m->ctx->device));
+	{ int rc0 = ensure_query_ws(m); if (rc0) return rc0; }
+	QueryWs *w = m->qws;
+	cudaStream_t st = m->ctx->streams[0];
+	for (int q = 0; q < mq; q++) memcpy(w->hQ + (size_t)q * m->d, pts + (size_t)q * ldp, sizeof(double) * m->d);
+	CUDA_TRY(cudaMemcpyAsync(w->dQ, w->hQ, sizeof(double) * (size_t)mq * m->d, cudaMemcpyHostToDevice, st));
+	int rc = predict_chunk(e, st, w->dQ, mq, w->dMean, w->dVar, true);
+	if (rc) return rc;
+	// mean and variance sit mqc apart: one copy of the first FEW_MAX of each
+	CUDA_TRY(cudaMemcpyAsync(w->hOut, w->dMean, sizeof(double) * mq, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpyAsync(w->hOut + FEW_MAX, w->dVar, sizeof(double) * mq, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	memcpy(mean, w->hOut, sizeof(double) * mq);
+	memcpy(var, w->hOut + FEW_MAX, sizeof(double) * mq);
+	return EMUB_OK;
+}
+
 // emulate_point_multi (multivar_support.c:103-157) for mq points: every PCA component's (mean, var) for the whole
 // chunk, then the back-projection to the nt observables on the device.  emus: nr emulators of ONE model.
 // mean / var: mq x nt row-major.  With nt = 0 the PCA-space values are returned instead (emulate_point_multi_pca,
 // multivar_support.c:78): mean / var are then mq x nr.
+static int predict_multi_impl(emub_emulator *const *emus, int nr, const double *pts, int ldp, int mq, int nt,
+                              const double *training_mean, const double *evecs, const double *evals, double *mean, double *var,
+                              bool few);
+
 extern "C" int emub_predict_multi(emub_emulator *const *emus, int nr, const double *pts, int ldp, int mq, int nt,
                                   const double *training_mean, const double *evecs, const double *evals, double *mean,
                                   double *var)
+{
+	return predict_multi_impl(emus, nr, pts, ldp, mq, nt, training_mean, evecs, evals, mean, var, false);
+}
+
+// the same for a handful of points (mq <= 8) on the latency path of every component (see emub_predict_few)
+extern "C" int emub_predict_multi_few(emub_emulator *const *emus, int nr, const double *pts, int ldp, int mq, int nt,
+                                      const double *training_mean, const double *evecs, const double *evals, double *mean,
+                                      double *var)
+{
+	if (mq > FEW_MAX) return set_err(EMUB_EINVAL, "emub_predict_multi_few: at most 8 points%s");
+	return predict_multi_impl(emus, nr, pts, ldp, mq, nt, training_mean, evecs, evals, mean, var, true);
+}
+
+static int predict_multi_impl(emub_emulator *const *emus, int nr, const double *pts, int ldp, int mq, int nt,
+                              const double *training_mean, const double *evecs, const double *evals, double *mean, double *var,
+                              bool few)
 {
 	if (!emus || nr < 1 || !pts || !mean || !var || mq < 0) return set_err(EMUB_EINVAL, "emub_predict_multi: bad argument%s");
 	emub_model *m = emus[0]->m;
@@ -1168,7 +1232,7 @@ extern "C" int emub_predict_multi(emub_emulator *const *emus, int nr, const doub
 	    m, pts, ldp, mq,
 	    [&](int cnt, const double *dQ, double *hOut) -> int {
 		    for (int j = 0; j < nr; j++) {
-			    int rc = predict_chunk(emus[j], st, dQ, cnt, w->dMean + (size_t)j * w->mqc, w->dVar + (size_t)j * w->mqc);
+			    int rc = predict_chunk(emus[j], st, dQ, cnt, w->dMean + (size_t)j * w->mqc, w->dVar + (size_t)j * w->mqc, few);
 			    if (rc) return rc;
 		    }
 		    if (nt > 0) {

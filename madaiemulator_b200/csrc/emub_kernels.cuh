@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(128) k_pred_final(const double *__restrict__ Q
                                                     const double *__restrict__ KA, int ncp, const double *__restrict__ vsq_part,
                                                     int nblk, int ldq, const double *__restrict__ beta,
                                                     const double *__restrict__ Minv, double kappa,
-                                                    double *__restrict__ mean, double *__restrict__ var)
+                                                    double *__restrict__ mean, double *__restrict__ var, int nka, long long ka_stride)
 {
 	__shared__ double sM[MAXNCP * MAXNCP];
 	__shared__ double sb[MAXNCP];
@@ -661,7 +661,13 @@ __global__ void __launch_bounds__(128) k_pred_final(const double *__restrict__ Q
 	const int q = blockIdx.x * blockDim.x + threadIdx.x;
 	if (q >= mq) return;
 	const double *x = Q + (size_t)q * d;
-	const double *ka = KA + (size_t)q * ncp;
+	// KA comes in nka partial sums (1 on the batched path)
+	double ka[MAXNCP + 1];
+	for (int c = 0; c <= p; c++) {
+		double s = 0.0;
+		for (int r = 0; r < nka; r++) s += KA[(size_t)r * ka_stride + (size_t)q * ncp + c];
+		ka[c] = s;
+	}
 	double rho[MAXNCP];
 	double hb = 0.0;
 	for (int c = 0; c < p; c++) {
@@ -685,6 +691,129 @@ __global__ void __launch_bounds__(128) k_pred_final(const double *__restrict__ Q
 	for (int k = 0; k < nblk; k++) vs += vsq_part[(size_t)k * ldq + q];
 	mean[q] = hb + ka[0];
 	var[q] = kappa - vs + reg;
+}
+
+// ---- a handful of query points (<= 8): latency path ---------------------------------------------------------
+// The batched pass multiplies W by a 128-column block of K: for one MCMC-style query that is a single wave of CTAs
+// each walking a K range of up to n, 220 us at n = 4096.  Here W K[:, 0:8] is a triangular matrix - skinny product
+// split over rows AND over chunks of FEW_JC columns of W (enough CTAs to stream W at memory speed), followed by
+// one CTA that adds the chunks up, squares, and forms the two small reductions of the prediction.
+constexpr int FEW_MAX = 8;      // query points per call on this path
+constexpr int FEW_JC = 512;     // columns of W per partial product
+
+// T[js][i][0..8) = sum_{j in chunk js, j <= i} W[i][j] K[j][0..8)     grid (npad/32, ceil(npad/FEW_JC)), 256 threads
+__global__ void __launch_bounds__(256) k_few_wk(const double *__restrict__ W, int ld, const double *__restrict__ K, int ldk,
+                                                double *__restrict__ T, int npad)
+{
+	const int js = blockIdx.y, j_lo = js * FEW_JC;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int r0 = blockIdx.x * 32 + warp * 4;
+	if (j_lo > r0 + 3) return;  // the chunk lies right of the diagonal for these rows
+	const int jend = min(j_lo + FEW_JC - 1, r0 + 3);
+	double acc[4][8];
+#pragma unroll
+	for (int r = 0; r < 4; r++)
+#pragma unroll
+		for (int c = 0; c < 8; c++) acc[r][c] = 0.0;
+	// four steps of 32 columns at a time, every load of the group issued before the first use (the loop bound is not
+	// a compile-time constant, so the compiler would not overlap the iterations on its own)
+	for (int jb = j_lo + lane; jb <= jend; jb += 128) {
+		double wv[4][4];
+		double4 v0[4], v1[4];
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const int j = jb + 32 * u;
+			const bool in = j <= jend;
+#pragma unroll
+			for (int r = 0; r < 4; r++) wv[u][r] = (in && j <= r0 + r) ? W[(size_t)(r0 + r) * ld + j] : 0.0;
+			v0[u] = in ? *reinterpret_cast<const double4 *>(K + (size_t)j * ldk) : make_double4(0.0, 0.0, 0.0, 0.0);
+			v1[u] = in ? *reinterpret_cast<const double4 *>(K + (size_t)j * ldk + 4) : make_double4(0.0, 0.0, 0.0, 0.0);
+		}
+#pragma unroll
+		for (int u = 0; u < 4; u++)
+#pragma unroll
+			for (int r = 0; r < 4; r++) {
+				const double w = wv[u][r];
+				acc[r][0] += w * v0[u].x; acc[r][1] += w * v0[u].y; acc[r][2] += w * v0[u].z; acc[r][3] += w * v0[u].w;
+				acc[r][4] += w * v1[u].x; acc[r][5] += w * v1[u].y; acc[r][6] += w * v1[u].z; acc[r][7] += w * v1[u].w;
+			}
+	}
+#pragma unroll
+	for (int r = 0; r < 4; r++)
+#pragma unroll
+		for (int c = 0; c < 8; c++) {
+			double s = acc[r][c];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+			acc[r][c] = s;
+		}
+	if (lane < 4) {
+		double *o = T + ((size_t)js * npad + r0 + lane) * 8;
+#pragma unroll
+		for (int r = 0; r < 4; r++)
+			if (lane == r)
+#pragma unroll
+				for (int c = 0; c < 8; c++) o[c] = acc[r][c];
+	}
+}
+
+// FEW_ROWS rows per CTA, one row per thread: partial vsq[blk][c] = sum_i (sum_js T[js][i][c])^2 and partial
+// KA[blk][c][pp] = sum_i K[i][c] AB[i][pp]   (c < 8, pp < ncp); k_pred_final adds the partials up.  grid npad / FEW_ROWS
+constexpr int FEW_ROWS = 128;
+__global__ void __launch_bounds__(FEW_ROWS) k_few_finish(const double *__restrict__ T, int npad, const double *__restrict__ K, int ldk,
+                                                         const double *__restrict__ AB, int ncp, double *__restrict__ vsq, int ldv,
+                                                         double *__restrict__ KA)
+{
+	__shared__ double red[FEW_ROWS / 32][65];
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int i = blockIdx.x * FEW_ROWS + tid;
+	double t[8];
+#pragma unroll
+	for (int c = 0; c < 8; c++) t[c] = 0.0;
+	const int nch = i / FEW_JC + 1;
+	for (int js = 0; js < nch; js++) {
+		const double4 a = *reinterpret_cast<const double4 *>(T + ((size_t)js * npad + i) * 8);
+		const double4 b = *reinterpret_cast<const double4 *>(T + ((size_t)js * npad + i) * 8 + 4);
+		t[0] += a.x; t[1] += a.y; t[2] += a.z; t[3] += a.w; t[4] += b.x; t[5] += b.y; t[6] += b.z; t[7] += b.w;
+	}
+#pragma unroll
+	for (int c = 0; c < 8; c++) {
+		double s = t[c] * t[c];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+		if (lane == 0) red[warp][c] = s;
+	}
+	__syncthreads();
+	if (tid < 8) {
+		double s = 0.0;
+		for (int w = 0; w < FEW_ROWS / 32; w++) s += red[w][tid];
+		vsq[(size_t)blockIdx.x * ldv + tid] = s;
+	}
+	const double4 k0 = *reinterpret_cast<const double4 *>(K + (size_t)i * ldk);
+	const double4 k1 = *reinterpret_cast<const double4 *>(K + (size_t)i * ldk + 4);
+	const double kv[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+	for (int p0 = 0; p0 < ncp; p0 += 8) {
+		const double4 a0 = *reinterpret_cast<const double4 *>(AB + (size_t)i * ncp + p0);
+		const double4 a1 = *reinterpret_cast<const double4 *>(AB + (size_t)i * ncp + p0 + 4);
+		const double av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+		__syncthreads();
+#pragma unroll
+		for (int c = 0; c < 8; c++)
+#pragma unroll
+			for (int q = 0; q < 8; q++) {
+				double s = kv[c] * av[q];
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+				if (lane == 0) red[warp][c * 8 + q] = s;
+			}
+		__syncthreads();
+		if (tid < 64) {
+			double s = 0.0;
+			for (int w = 0; w < FEW_ROWS / 32; w++) s += red[w][tid];
+			const int c = tid >> 3, q = tid & 7;
+			KA[((size_t)blockIdx.x * 8 + c) * ncp + p0 + q] = s;
+		}
+	}
 }
 
 // PCA back-projection (multivar_support.c:126-151): mean_i = ybar_i + sum_j U_ij sqrt(lambda_j) m_j,

@@ -30,10 +30,10 @@ SYMBOLS = [
     "emub_ctx_create", "emub_ctx_destroy", "emub_last_error", "emub_version", "emub_ctx_stream",
     "emub_ctx_set_groups", "emub_ctx_use_graphs", "emub_model_create", "emub_model_destroy", "emub_model_nthetas",
     "emub_model_nregression_fns", "emub_model_slots", "emub_model_set_training", "emub_model_set_training_multi",
-    "emub_model_ncomponents", "emub_model_set_gradient_mode", "emub_model_gradient_mode", "emub_loglik_grad_batch_comp", "emub_emulator_create_comp", "emub_predict_multi", "emub_cov_matrix",
+    "emub_model_ncomponents", "emub_model_set_gradient_mode", "emub_model_gradient_mode", "emub_loglik_grad_batch_comp", "emub_emulator_create_comp", "emub_predict_multi", "emub_predict_multi_few", "emub_cov_matrix",
     "emub_h_matrix", "emub_k_vectors", "emub_loglik_grad_batch", "emub_loglik_grad_batch_dev",
     "emub_ctx_synchronize", "emub_loglik_extras", "emub_emulator_create", "emub_emulator_destroy",
-    "emub_emulator_beta", "emub_predict_batch", "emub_predict_batch_dev", "emub_profile_enable",
+    "emub_emulator_beta", "emub_predict_batch", "emub_predict_few", "emub_predict_batch_dev", "emub_profile_enable",
     "emub_profile_reset", "emub_profile_read", "emub_profile_name", "emub_launch_count", "emub_debug_fetch",
     "emub_debug_cholesky", "emub_debug_exp",
 ]
@@ -83,6 +83,7 @@ def lib():
     L.emub_loglik_grad_batch_comp.argtypes = [_vp, _dp, _ip, _ci, _ci, _dp, _dp, _dp, _ip]
     L.emub_emulator_create_comp.argtypes = [_vp, _ci, _dp, ctypes.POINTER(_vp)]
     L.emub_predict_multi.argtypes = [ctypes.POINTER(_vp), _ci, _dp, _ci, _ci, _ci, _dp, _dp, _dp, _dp, _dp]
+    L.emub_predict_multi_few.argtypes = [ctypes.POINTER(_vp), _ci, _dp, _ci, _ci, _ci, _dp, _dp, _dp, _dp, _dp]
     L.emub_cov_matrix.argtypes = [_vp, _dp, _dp, _ci]
     L.emub_h_matrix.argtypes = [_vp, _dp, _ci]
     L.emub_k_vectors.argtypes = [_vp, _dp, _dp, _ci, _ci, _dp, _ci]
@@ -94,6 +95,7 @@ def lib():
     L.emub_emulator_destroy.restype = None
     L.emub_emulator_beta.argtypes = [_vp, _dp]
     L.emub_predict_batch.argtypes = [_vp, _dp, _ci, _ci, _dp, _dp]
+    L.emub_predict_few.argtypes = [_vp, _dp, _ci, _ci, _dp, _dp]
     L.emub_predict_batch_dev.argtypes = [_vp, _vp, _ci, _vp, _vp]
     L.emub_profile_enable.argtypes = [_vp, _ci]
     L.emub_profile_reset.argtypes = [_vp]
@@ -297,6 +299,14 @@ class Emulator:
         _check(self.L.emub_predict_batch(self.h, _P(pts), self.model.d, m, _P(mean), _P(var)))
         return mean, var
 
+    def emulate_few(self, pts):
+        """emub_predict_few: the latency path for at most 8 points"""
+        pts = _c(pts).reshape(-1, self.model.d)
+        m = pts.shape[0]
+        mean, var = np.empty(m), np.empty(m)
+        _check(self.L.emub_predict_few(self.h, _P(pts), self.model.d, m, _P(mean), _P(var)))
+        return mean, var
+
     def emulate_dev(self, d_pts_ptr, m, d_mean_ptr, d_var_ptr):
         _check(self.L.emub_predict_batch_dev(self.h, d_pts_ptr, m, d_mean_ptr, d_var_ptr))
 
@@ -317,11 +327,12 @@ class Emulator:
             pass
 
 
-def predict_multi(emulators, pts, training_mean=None, evecs=None, evals=None):
+def predict_multi(emulators, pts, training_mean=None, evecs=None, evals=None, few=False):
     """emulate_point_multi (multivar_support.c:103) for a block of points: emulators = the nr PCA-component
     emulators of ONE model.  With the projection data returns (mean, var) of shape (m, nt) in observable space;
-    without it the PCA-space values (m, nr) (emulate_point_multi_pca)."""
+    without it the PCA-space values (m, nr) (emulate_point_multi_pca).  few=True: the latency path for <= 8 points."""
     model = emulators[0].model
+    fn = model.L.emub_predict_multi_few if few else model.L.emub_predict_multi
     pts = _c(pts).reshape(-1, model.d)
     m, nr = pts.shape[0], len(emulators)
     arr = (_vp * nr)(*[em.h for em in emulators])
@@ -329,11 +340,10 @@ def predict_multi(emulators, pts, training_mean=None, evecs=None, evals=None):
         evecs = _c(evecs).reshape(-1, nr)
         nt = evecs.shape[0]
         mean, var = np.empty((m, nt)), np.empty((m, nt))
-        _check(model.L.emub_predict_multi(arr, nr, _P(pts), model.d, m, nt, _P(_c(training_mean)), _P(evecs), _P(_c(evals)),
-                                          _P(mean), _P(var)))
+        _check(fn(arr, nr, _P(pts), model.d, m, nt, _P(_c(training_mean)), _P(evecs), _P(_c(evals)), _P(mean), _P(var)))
     else:
         mean, var = np.empty((m, nr)), np.empty((m, nr))
-        _check(model.L.emub_predict_multi(arr, nr, _P(pts), model.d, m, 0, None, None, None, _P(mean), _P(var)))
+        _check(fn(arr, nr, _P(pts), model.d, m, 0, None, None, None, _P(mean), _P(var)))
     return mean, var
 
 
@@ -342,7 +352,7 @@ HOST_LIB_PATH = os.path.join(_HERE, "host", "libemuhost.so")
 HOST_SYMBOLS = ["emub_estimate_default_opts", "emub_sample_scales", "emub_optimization_ranges", "emub_random_init",
                 "emub_estimate_thetas", "emub_estimate_thetas_from", "emub_estimate_thetas_multi", "emub_estimate_thetas_multi_devices", "emub_estimate_thetas_multi_devices_ranges", "emub_snapshot_load",
                 "emub_snapshot_load_path", "emub_snapshot_free", "emub_multi_emulator_from_snapshot",
-                "emub_multi_emulator_destroy", "emub_multi_emulator_predict", "emub_interactive_stream", "emub_parse_doubles",
+                "emub_multi_emulator_destroy", "emub_multi_emulator_predict", "emub_multi_emulator_predict_few", "emub_interactive_stream", "emub_parse_doubles",
                 "emub_snapshot_save", "emub_snapshot_save_path", "emub_snapshot_from_arrays"]
 
 

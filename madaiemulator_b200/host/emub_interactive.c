@@ -152,6 +152,24 @@ int emub_multi_emulator_predict(emub_multi_emulator *me, const double *pts, int 
 	return rc;
 }
 
+/* emulate_point_multi[_pca] for a handful of points (m <= 8): the latency path on the first device */
+int emub_multi_emulator_predict_few(emub_multi_emulator *me, const double *pts, int m, int pca_output, double *mean, double *var)
+{
+	if (!me || !pts || !mean || !var || m < 0 || m > 8) return EMUB_EINVAL;
+	if (!pca_output)
+		return emub_predict_multi_few(me->emus, me->nr, pts, me->d, m, me->nt, me->training_mean, me->evecs, me->evals, mean, var);
+	double pm[8 * 64], pv[8 * 64];
+	if (me->nr > 64) return emub_multi_emulator_predict(me, pts, m, pca_output, mean, var);
+	int rc = emub_predict_multi_few(me->emus, me->nr, pts, me->d, m, 0, NULL, NULL, NULL, pm, pv);
+	if (rc == EMUB_OK)
+		for (int q = 0; q < m; q++)
+			for (int i = 0; i < me->nt; i++) {
+				mean[(size_t)q * me->nt + i] = i < me->nr ? pm[(size_t)q * me->nr + i] : 0.0;
+				var[(size_t)q * me->nt + i] = i < me->nr ? pv[(size_t)q * me->nr + i] : 0.0;
+			}
+	return rc;
+}
+
 static int predict_one(emub_multi_emulator *me, const double *pts, int m, int pca_output, double *mean, double *var)
 {
 	if (!pca_output)

@@ -31,6 +31,10 @@ int emub_multi_emulator_nparams(const emub_multi_emulator *me);
 /* emulate_point_multi / _pca for a block: mean, var are m x nt (pca_output: first nr of each row are meaningful) */
 int emub_multi_emulator_predict(emub_multi_emulator *me, const double *pts, int m, int pca_output, double *mean, double *var);
 
+/* the same for at most 8 points on the latency path (emub_predict_multi_few): what a point-by-point caller -- the
+ * reference's interactive loop, an MCMC driver behind EmuPlusPlus -- should use */
+int emub_multi_emulator_predict_few(emub_multi_emulator *me, const double *pts, int m, int pca_output, double *mean, double *var);
+
 /* Text -> doubles, the input side of the stream: buf[0, len) must end on a separator (blank, newline, tab, CR, comma)
  * or be the end of the input, and buf[len] must be writable.  Converts up to max values with strtod (the same
  * conversion as the reference's fscanf("%lf")), tokens counted and converted on `threads` host threads when the text

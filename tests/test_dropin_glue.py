@@ -60,7 +60,8 @@ def test_point_list_entry_points_run_on_the_engine(oracles, name):
     assert relerr(m2, m1, 1e-3) < 1e-9
     assert np.max(np.abs(v2 - v1)) < 1e-9 * max(1.0, float(c["kappa"]))
     m3, v3 = dro.emulate_at_point_list(c["theta_full"], pts[:5], single=True)
-    assert np.array_equal(m3, m2[:5]) and np.array_equal(v3, v2[:5])
+    # single points take the latency path (emub_predict_few): the same sums in another order
+    assert relerr(m3, m2[:5], 1e-3) < 1e-11 and np.max(np.abs(v3 - v2[:5])) < 1e-11 * max(1.0, float(c["kappa"]))
 
 
 def test_glue_recognises_a_model_by_its_contents(oracles):

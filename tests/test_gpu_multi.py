@@ -111,6 +111,11 @@ def test_predict_multi_many_observables(ctx):
     assert np.max(np.abs(var - ev)) < 1e-12 * max(1.0, np.max(np.abs(ev)))
     mp2, vp2 = engine.predict_multi(emus, pts)
     assert np.array_equal(mp, mp2) and np.array_equal(vp, vp2)
+    # the latency path for a handful of points: same answers to rounding, in both output spaces
+    mf, vf = engine.predict_multi(emus, pts[:3], ybar, U, lam, few=True)
+    assert np.max(np.abs(mf - mean[:3])) < 1e-11 * max(1.0, np.max(np.abs(mean))) and np.max(np.abs(vf - var[:3])) < 1e-11 * max(1.0, np.max(np.abs(var)))
+    mf, vf = engine.predict_multi(emus, pts[:1], few=True)
+    assert np.max(np.abs(mf - mp[:1])) < 1e-11 and np.max(np.abs(vf - vp[:1])) < 1e-11
     with pytest.raises(engine.EmubError):
         engine.predict_multi(emus, pts, np.zeros(2000), np.zeros((2000, nr)), lam)
     for e in emus:

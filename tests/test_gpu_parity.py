@@ -368,3 +368,33 @@ def test_exact_gradient_mode_is_the_derivative_of_the_objective(ctx, n, d, order
     if kernel == 1 and d > 1:
         assert np.max(np.abs(lit["grad"][0] - fd) / scale) > 1e-3  # the literal formula is something else
     m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,d,order,kernel", [(40, 1, 1, 1), (129, 3, 3, 1), (700, 15, 1, 1), (1500, 6, 2, 3), (2100, 4, 0, 2)])
+def test_few_points_latency_path(ctx, n, d, order, kernel):
+    """emub_predict_few (<= 8 points, the per-point call pattern of emulate_point): same quantities as the batched
+    pass, summed in another order -- 1e-9 against the oracle, ~1e-14 against emub_predict_batch; a query on a design
+    point (coincidence nugget), every count from 1 to 8, the 9th is refused."""
+    from madaiemulator_b200 import engine
+    X = ds.synthetic_design(n, d)
+    y = ds.synthetic_response(X)
+    m = engine.Model(ctx, X, y, kernel, order, max_slots=1)
+    full = np.concatenate([[0.2, -3.0], np.full(d, 0.7)]) if kernel == 1 else np.array([1.3, 0.05, 0.6])
+    e = m.emulator(full)
+    oe = _oracle(X, y, kernel, order).emulator(full)
+    pts = ds.synthetic_queries(8, d)
+    pts[2] = X[n // 3]
+    kappa = _oracle(X, y, kernel, order).cov_pair(pts[0], pts[0], full)
+    mb, vb = e.emulate(pts)
+    for cnt in (1, 2, 5, 8):
+        mf, vf = e.emulate_few(pts[:cnt])
+        mo, vo = oe.emulate(pts[:cnt])
+        assert relerr(mf, mo, 1e-3) < TOL
+        assert np.max(np.abs(vf - vo)) < TOL * max(1.0, kappa)
+        assert np.max(np.abs(mf - mb[:cnt])) < 1e-11 * max(1.0, np.max(np.abs(mb)))
+        assert np.max(np.abs(vf - vb[:cnt])) < 1e-11 * max(1.0, kappa)
+    with pytest.raises(engine.EmubError):
+        e.emulate_few(ds.synthetic_queries(9, d))
+    e.close()
+    m.close()
