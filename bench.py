@@ -287,6 +287,16 @@ def main():
         mean_h, var_h = emu.emulate(pts)
     t_pe = max_over_ranks(time.perf_counter() - t0)
     pred_e2e = world * mq * psteps / t_pe
+    # latency of the per-point call pattern (emulate_point through the glue -> emub_predict_few), host pointers, rank 0
+    single_us = None
+    if rank == 0:
+        one = pts[:1].copy()
+        for _ in range(10):
+            emu.emulate_few(one)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            emu.emulate_few(one)
+        single_us = (time.perf_counter() - t0) / 200 * 1e6
 
     out = None
     if rank == 0:
@@ -357,7 +367,8 @@ def main():
                                                    "e2e": {"value": pred_e2e, "unit": "points/s",
                                                            "h2d_bytes_per_step": int(mq * D_MODEL * 8), "d2h_bytes_per_step": int(mq * 16)},
                                                    "roofline": pred_roof,
-                                                   "algorithmic_flops_per_point": float(N_MODEL) ** 2 + 2 * N_MODEL + 3 * N_MODEL * D_MODEL}}}
+                                                   "algorithmic_flops_per_point": float(N_MODEL) ** 2 + 2 * N_MODEL + 3 * N_MODEL * D_MODEL},
+                         "single_point_call_us": {"value": single_us, "unit": "us per emub_predict_few call (host pointers, 1 point)"}}}
     emu.close()
     model.close()
     ctx.close()
