@@ -126,6 +126,12 @@ struct QueryWs {
 	int ncomp;    // rows of dMean / dVar
 	double *dQ, *dK, *dVsq, *dKA, *dMean, *dVar;  // dMean, dVar: ncomp x mqc
 	double *dFew;                                 // partial products of the few-points path: [ceil(npad/FEW_JC)][npad][8]
+	unsigned long long proj_hash;                 // contents of dProj (0: none), so a point-by-point caller uploads it once
+	// several emulators answered by one set of launches on the few-points path (predict_few_set)
+	FewSet *dFewSet;
+	double *dFewConsts;                           // [few_cap][CONST_STRIDE], contiguous copy of the emulators' constants
+	int few_cap;                                  // emulators dFewSet / dFewConsts / dFew hold
+	unsigned long long few_hash;                  // which emulators the tables describe (0: none)
 	double *dOutM, *dOutV, *dProj;                // back-projected outputs (mqc x ntmax), projection data
 	GemmTask *dTasks;
 	double *hQ, *hOut;  // pinned
@@ -402,6 +408,7 @@ static void free_query_ws(emub_model *m)
 	if (!w) return;
 	cudaFree(w->dQ); cudaFree(w->dK); cudaFree(w->dVsq); cudaFree(w->dKA); cudaFree(w->dMean); cudaFree(w->dVar);
 	cudaFree(w->dOutM); cudaFree(w->dOutV); cudaFree(w->dProj); cudaFree(w->dTasks); cudaFree(w->dFew);
+	cudaFree(w->dFewSet); cudaFree(w->dFewConsts);
 	cudaFreeHost(w->hQ); cudaFreeHost(w->hOut);
 	cudaFree(w->dQb[1]); cudaFreeHost(w->hQb[1]); cudaFreeHost(w->hOutb[1]);
 	if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
@@ -912,6 +919,7 @@ static int ensure_query_ws(emub_model *m)
 	CUDA_TRY(cudaMalloc(&w->dMean, sizeof(double) * (size_t)w->ncomp * mqc));
 	CUDA_TRY(cudaMalloc(&w->dVar, sizeof(double) * (size_t)w->ncomp * mqc));
 	CUDA_TRY(cudaMalloc(&w->dFew, sizeof(double) * (size_t)((m->npad + FEW_JC - 1) / FEW_JC) * m->npad * 8));
+	w->few_cap = 1;
 	w->ntcap = NTMAX;
 	CUDA_TRY(cudaMalloc(&w->dOutM, sizeof(double) * (size_t)NTMAX * mqc));
 	CUDA_TRY(cudaMalloc(&w->dOutV, sizeof(double) * (size_t)NTMAX * mqc));
@@ -946,6 +954,7 @@ static int ensure_output_capacity(emub_model *m, int need)
 	cudaFree(w->dOutM); cudaFree(w->dOutV); cudaFree(w->dProj);
 	cudaFreeHost(w->hOutb[0]); cudaFreeHost(w->hOutb[1]);
 	w->dOutM = w->dOutV = w->dProj = nullptr;
+	w->proj_hash = 0;
 	w->hOut = w->hOutb[0] = w->hOutb[1] = nullptr;
 	w->ntcap = 0;
 	CUDA_TRY(cudaMalloc(&w->dOutM, sizeof(double) * (size_t)cap * w->mqc));
@@ -1041,16 +1050,16 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 		// latency path: W K[:, 0:8] as a row- and column-split skinny product, one CTA for the reductions
 		{
 			LaunchScope ls(c, EMUB_K_GEMM_PRED, (double)m->npad * m->npad * 8, st);
-			k_few_wk<<<dim3(m->npad / 32, (m->npad + FEW_JC - 1) / FEW_JC), 256, 0, st>>>(e->W, m->npad, w->dK, ldk, w->dFew, m->npad);
+			k_few_wk<<<dim3(m->npad / 32, (m->npad + FEW_JC - 1) / FEW_JC), 256, 0, st>>>(e->W, m->npad, w->dK, ldk, w->dFew, m->npad, nullptr, 0, 0);
 		}
 		{
 			LaunchScope ls(c, EMUB_K_SKINNY, 8.0 * (double)m->npad * (8 + m->ncp), st);
-			k_few_finish<<<m->npad / FEW_ROWS, FEW_ROWS, 0, st>>>(w->dFew, m->npad, w->dK, ldk, e->AB, m->ncp, w->dVsq, ldk, w->dKA);
+			k_few_finish<<<m->npad / FEW_ROWS, FEW_ROWS, 0, st>>>(w->dFew, m->npad, w->dK, ldk, e->AB, m->ncp, w->dVsq, ldk, w->dKA, nullptr, 0, 0, 0);
 		}
 		{
 			LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);
 			k_pred_final<<<1, 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, m->npad / FEW_ROWS, ldk, e->beta, e->Minv,
-			                                e->kappa, dMean, dVar, m->npad / FEW_ROWS, (long long)FEW_MAX * m->ncp);
+			                                e->kappa, dMean, dVar, m->npad / FEW_ROWS, (long long)FEW_MAX * m->ncp, nullptr, 0, 0);
 		}
 		CUDA_TRY(cudaGetLastError());
 		return EMUB_OK;
@@ -1067,7 +1076,86 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 	{
 		LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);
 		k_pred_final<<<(mq + 127) / 128, 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, m->nblk * DefaultCfg::SUBM, ldk, e->beta,
-		                                               e->Minv, e->kappa, dMean, dVar, 1, 0);
+		                                               e->Minv, e->kappa, dMean, dVar, 1, 0, nullptr, 0, 0);
+	}
+	CUDA_TRY(cudaGetLastError());
+	return EMUB_OK;
+}
+
+// The few-points path for nr emulators of one model at once: every kernel carries the component in its grid, so a
+// point of a multivariate model costs 4 launches instead of 4 per component.  dMean / dVar: [nr][mqc].
+static bool few_set_fits(const emub_model *m, int nr)
+{
+	const QueryWs *w = m->qws;
+	const long long nparts = m->npad / FEW_ROWS;
+	return (long long)nr * TB <= w->mqc && (long long)nr * nparts * FEW_MAX <= w->mqc;
+}
+
+static int predict_few_set(emub_emulator *const *emus, int nr, cudaStream_t st, const double *dQ, int mq, double *dMean, double *dVar)
+{
+	emub_model *m = emus[0]->m;
+	emub_ctx *c = m->ctx;
+	QueryWs *w = m->qws;
+	const int ldk = w->mqc;
+	const int nsplit = (m->npad + FEW_JC - 1) / FEW_JC, nparts = m->npad / FEW_ROWS;
+	const long long tstride = (long long)nsplit * m->npad * 8, kastride = (long long)nparts * FEW_MAX * m->ncp;
+	// tables: rebuilt when the set of emulators (their device buffers) changes
+	unsigned long long h = 1469598103934665603ull ^ (unsigned long long)nr;
+	std::vector<FewSet> hs((size_t)nr);
+	for (int j = 0; j < nr; j++) {
+		hs[j] = FewSet{emus[j]->W, emus[j]->AB, emus[j]->beta, emus[j]->Minv, emus[j]->kappa};
+		const unsigned long long words[6] = {(unsigned long long)(uintptr_t)emus[j]->W, (unsigned long long)(uintptr_t)emus[j]->AB,
+		                                     (unsigned long long)(uintptr_t)emus[j]->beta, (unsigned long long)(uintptr_t)emus[j]->Minv,
+		                                     (unsigned long long)(uintptr_t)emus[j]->consts, 0};
+		for (int k = 0; k < 5; k++) h = (h ^ words[k]) * 1099511628211ull;
+		unsigned long long bits;
+		memcpy(&bits, &emus[j]->kappa, sizeof(bits));
+		h = (h ^ bits) * 1099511628211ull;
+	}
+	if (h == 0) h = 1;
+	if (h != w->few_hash) {
+		w->few_hash = 0;
+		if (nr > w->few_cap || !w->dFewSet) {
+			CUDA_TRY(cudaStreamSynchronize(st));
+			cudaFree(w->dFewSet); cudaFree(w->dFewConsts); cudaFree(w->dFew);
+			w->dFewSet = nullptr; w->dFewConsts = nullptr; w->dFew = nullptr;
+			w->few_cap = 0;
+			CUDA_TRY(cudaMalloc(&w->dFewSet, sizeof(FewSet) * (size_t)nr));
+			CUDA_TRY(cudaMalloc(&w->dFewConsts, sizeof(double) * (size_t)nr * CONST_STRIDE));
+			CUDA_TRY(cudaMalloc(&w->dFew, sizeof(double) * (size_t)nr * tstride));
+			w->few_cap = nr;
+		}
+		CUDA_TRY(cudaMemcpyAsync(w->dFewSet, hs.data(), sizeof(FewSet) * (size_t)nr, cudaMemcpyHostToDevice, st));
+		for (int j = 0; j < nr; j++)
+			CUDA_TRY(cudaMemcpyAsync(w->dFewConsts + (size_t)j * CONST_STRIDE, emus[j]->consts, sizeof(double) * CONST_STRIDE,
+			                         cudaMemcpyDeviceToDevice, st));
+		CUDA_TRY(cudaStreamSynchronize(st));  // hs is a local
+		w->few_hash = h;
+	}
+	{
+		// cross covariances of every component: component z at the columns [128 z, 128 z + 128) of dK
+		const size_t smem = 2 * (size_t)m->d * CT * sizeof(double);
+		LaunchScope ls(c, EMUB_K_KCROSS, 8.0 * (double)m->npad * TB * nr, st);
+		dim3 grid(TB / CT, m->npad / CT, nr);
+		switch (m->kernel) {
+		case 2: k_cov<2, true><<<grid, 256, smem, st>>>(m->dX, m->n, m->d, dQ, mq, w->dFewConsts, CONST_STRIDE, w->dK, TB, ldk, 0); break;
+		case 3: k_cov<3, true><<<grid, 256, smem, st>>>(m->dX, m->n, m->d, dQ, mq, w->dFewConsts, CONST_STRIDE, w->dK, TB, ldk, 0); break;
+		default: k_cov<1, true><<<grid, 256, smem, st>>>(m->dX, m->n, m->d, dQ, mq, w->dFewConsts, CONST_STRIDE, w->dK, TB, ldk, 0); break;
+		}
+	}
+	{
+		LaunchScope ls(c, EMUB_K_GEMM_PRED, (double)m->npad * m->npad * 8 * nr, st);
+		k_few_wk<<<dim3(m->npad / 32, nsplit, nr), 256, 0, st>>>(nullptr, m->npad, w->dK, ldk, w->dFew, m->npad, w->dFewSet, TB, tstride);
+	}
+	{
+		LaunchScope ls(c, EMUB_K_SKINNY, 8.0 * (double)m->npad * (8 + m->ncp) * nr, st);
+		k_few_finish<<<dim3(nparts, nr), FEW_ROWS, 0, st>>>(w->dFew, m->npad, w->dK, ldk, nullptr, m->ncp, w->dVsq, ldk, w->dKA, w->dFewSet, TB,
+		                                                    tstride, kastride);
+	}
+	{
+		LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);
+		k_pred_final<<<dim3(1, nr), 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, nparts, ldk, nullptr, nullptr, 0.0, dMean,
+		                                          dVar, nparts, (long long)FEW_MAX * m->ncp, w->dFewSet, kastride, w->mqc);
 	}
 	CUDA_TRY(cudaGetLastError());
 	return EMUB_OK;
@@ -1220,20 +1308,36 @@ static int predict_multi_impl(emub_emulator *const *emus, int nr, const double *
 	{ int rc1 = ensure_output_capacity(m, std::max(nt, nr)); if (rc1) return rc1; }
 	cudaStream_t st = m->ctx->streams[0];
 	if (nt > 0) {
-		// projection data: ybar[nt] | evecs[nt x nr] | evals[nr]
+		// projection data: ybar[nt] | evecs[nt x nr] | evals[nr]; uploaded when it differs from what dProj holds
 		std::vector<double> proj((size_t)nt + (size_t)nt * nr + nr);
 		memcpy(proj.data(), training_mean, sizeof(double) * nt);
 		memcpy(proj.data() + nt, evecs, sizeof(double) * (size_t)nt * nr);
 		memcpy(proj.data() + nt + (size_t)nt * nr, evals, sizeof(double) * nr);
-		CUDA_TRY(cudaMemcpy(w->dProj, proj.data(), sizeof(double) * proj.size(), cudaMemcpyHostToDevice));
+		unsigned long long h = 1469598103934665603ull ^ ((unsigned long long)nt << 32 | (unsigned)nr);
+		for (double v : proj) {
+			unsigned long long bits;
+			memcpy(&bits, &v, sizeof(bits));
+			h = (h ^ bits) * 1099511628211ull;
+		}
+		if (h == 0) h = 1;
+		if (h != w->proj_hash) {
+			w->proj_hash = 0;
+			CUDA_TRY(cudaMemcpy(w->dProj, proj.data(), sizeof(double) * proj.size(), cudaMemcpyHostToDevice));
+			w->proj_hash = h;
+		}
 	}
 	const size_t vofs = (size_t)w->ntcap * w->mqc;  // variances start here in a host output buffer
 	return walk_query_chunks(
 	    m, pts, ldp, mq,
 	    [&](int cnt, const double *dQ, double *hOut) -> int {
-		    for (int j = 0; j < nr; j++) {
-			    int rc = predict_chunk(emus[j], st, dQ, cnt, w->dMean + (size_t)j * w->mqc, w->dVar + (size_t)j * w->mqc, few);
+		    if (few && nr > 1 && cnt <= FEW_MAX && few_set_fits(m, nr)) {
+			    int rc = predict_few_set(emus, nr, st, dQ, cnt, w->dMean, w->dVar);
 			    if (rc) return rc;
+		    } else {
+			    for (int j = 0; j < nr; j++) {
+				    int rc = predict_chunk(emus[j], st, dQ, cnt, w->dMean + (size_t)j * w->mqc, w->dVar + (size_t)j * w->mqc, few);
+				    if (rc) return rc;
+			    }
 		    }
 		    if (nt > 0) {
 			    {

@@ -16,6 +16,13 @@ constexpr int MAXD = 32;     // nparams limit (smem staging of design rows)
 constexpr int MAXNCP = 48;   // 1 + nregression_fns, padded to a multiple of 8
 constexpr int CT = 64;       // covariance / gradient tile edge
 
+// few-points prediction path (k_few_*, k_pred_final): one entry per emulator (PCA component) when several are answered
+// by the same launches (component = blockIdx.z / .y)
+struct FewSet {
+	const double *W, *AB, *beta, *Minv;
+	double kappa;
+};
+
 // per-point constants derived from theta, layout (stride CONST_STRIDE doubles):
 //  [0] amp  [1] nugget  [2] rho (Matern)  [3] sigma2 slot (filled later)
 //  [4 .. 4+d)       1 / (exp(theta_k))^2               emulator.c:123-127
@@ -651,8 +658,19 @@ __global__ void __launch_bounds__(128) k_pred_final(const double *__restrict__ Q
                                                     const double *__restrict__ KA, int ncp, const double *__restrict__ vsq_part,
                                                     int nblk, int ldq, const double *__restrict__ beta,
                                                     const double *__restrict__ Minv, double kappa,
-                                                    double *__restrict__ mean, double *__restrict__ var, int nka, long long ka_stride)
+                                                    double *__restrict__ mean, double *__restrict__ var, int nka, long long ka_stride,
+                                                    const FewSet *__restrict__ set, long long kastride_z, int mstride)
 {
+	if (set) {  // component z = blockIdx.y of a few-points call over several emulators
+		const int z = blockIdx.y;
+		beta = set[z].beta;
+		Minv = set[z].Minv;
+		kappa = set[z].kappa;
+		KA += (size_t)z * kastride_z;
+		vsq_part += (size_t)z * 8;
+		mean += (size_t)z * mstride;
+		var += (size_t)z * mstride;
+	}
 	__shared__ double sM[MAXNCP * MAXNCP];
 	__shared__ double sb[MAXNCP];
 	for (int i = threadIdx.x; i < p * p; i += blockDim.x) sM[i] = Minv[(i / p) * MAXNCP + (i % p)];
@@ -702,9 +720,16 @@ constexpr int FEW_MAX = 8;      // query points per call on this path
 constexpr int FEW_JC = 512;     // columns of W per partial product
 
 // T[js][i][0..8) = sum_{j in chunk js, j <= i} W[i][j] K[j][0..8)     grid (npad/32, ceil(npad/FEW_JC)), 256 threads
+// set != null: component z = blockIdx.z uses set[z].W, the columns [z * kstride, ..) of K and T + z * tstride
 __global__ void __launch_bounds__(256) k_few_wk(const double *__restrict__ W, int ld, const double *__restrict__ K, int ldk,
-                                                double *__restrict__ T, int npad)
+                                                double *__restrict__ T, int npad, const FewSet *__restrict__ set, int kstride,
+                                                long long tstride)
 {
+	if (set) {
+		W = set[blockIdx.z].W;
+		K += (size_t)blockIdx.z * kstride;
+		T += (size_t)blockIdx.z * tstride;
+	}
 	const int js = blockIdx.y, j_lo = js * FEW_JC;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int r0 = blockIdx.x * 32 + warp * 4;
@@ -760,10 +785,20 @@ __global__ void __launch_bounds__(256) k_few_wk(const double *__restrict__ W, in
 // FEW_ROWS rows per CTA, one row per thread: partial vsq[blk][c] = sum_i (sum_js T[js][i][c])^2 and partial
 // KA[blk][c][pp] = sum_i K[i][c] AB[i][pp]   (c < 8, pp < ncp); k_pred_final adds the partials up.  grid npad / FEW_ROWS
 constexpr int FEW_ROWS = 128;
+// set != null: component z = blockIdx.y; its vsq partials go to the columns [8 z, 8 z + 8), its KA partials to KA + z * kastride
 __global__ void __launch_bounds__(FEW_ROWS) k_few_finish(const double *__restrict__ T, int npad, const double *__restrict__ K, int ldk,
                                                          const double *__restrict__ AB, int ncp, double *__restrict__ vsq, int ldv,
-                                                         double *__restrict__ KA)
+                                                         double *__restrict__ KA, const FewSet *__restrict__ set, int kstride,
+                                                         long long tstride, long long kastride)
 {
+	if (set) {
+		const int z = blockIdx.y;
+		AB = set[z].AB;
+		K += (size_t)z * kstride;
+		T += (size_t)z * tstride;
+		vsq += (size_t)z * 8;
+		KA += (size_t)z * kastride;
+	}
 	__shared__ double red[FEW_ROWS / 32][65];
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int i = blockIdx.x * FEW_ROWS + tid;

@@ -40,3 +40,24 @@ for n, d in ((4096, 10), (1024, 10), (100, 3)):
         print("n=%d m=%d: %.1f us per call (%.0f points/s) | " % (n, mq, us, mq / us * 1e6) +
               ", ".join("%s %.1f us" % (k, v["ms"] * 1e3) for k, v in prof.items() if v["launches"]))
     e.close(); m.close()
+
+# all PCA components of one model + back-projection for one point (emulate_point_multi in the glue)
+for n, d, nr, nt in ((100, 3, 5, 6), (1024, 10, 8, 12)):
+    X = ds.synthetic_design(n, d)
+    rng = np.random.default_rng(2)
+    Z = rng.normal(size=(n, nr))
+    m = engine.Model(ctx, X, Z[:, 0], 1, 0, max_slots=1)
+    m.set_training_multi(Z)
+    emus = [m.emulator(np.concatenate([[0.0], ds.default_theta_less_amp(d)]), comp=c) for c in range(nr)]
+    ybar, U, lam = rng.normal(size=nt), rng.normal(size=(nt, nr)), rng.uniform(0.5, 2, nr)
+    one = ds.synthetic_queries(1, d)
+    for few in (False, True):
+        for _ in range(5):
+            engine.predict_multi(emus, one, ybar, U, lam, few=few)
+        t0 = time.time()
+        for _ in range(200):
+            engine.predict_multi(emus, one, ybar, U, lam, few=few)
+        print("multi n=%d nr=%d nt=%d one point, %s path: %.1f us per call" % (n, nr, nt, "few" if few else "batched", (time.time() - t0) / 200 * 1e6))
+    for e in emus:
+        e.close()
+    m.close()
