@@ -1050,7 +1050,9 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 		// latency path: W K[:, 0:8] as a row- and column-split skinny product, one CTA for the reductions
 		{
 			LaunchScope ls(c, EMUB_K_GEMM_PRED, (double)m->npad * m->npad * 8, st);
-			k_few_wk<<<dim3(m->npad / 32, (m->npad + FEW_JC - 1) / FEW_JC), 256, 0, st>>>(e->W, m->npad, w->dK, ldk, w->dFew, m->npad, nullptr, 0, 0);
+			const dim3 grid(m->npad / 32, (m->npad + FEW_JC - 1) / FEW_JC);
+			if (mq == 1) k_few_wk<1><<<grid, 256, 0, st>>>(e->W, m->npad, w->dK, ldk, w->dFew, m->npad, nullptr, 0, 0);
+			else k_few_wk<8><<<grid, 256, 0, st>>>(e->W, m->npad, w->dK, ldk, w->dFew, m->npad, nullptr, 0, 0);
 		}
 		{
 			LaunchScope ls(c, EMUB_K_SKINNY, 8.0 * (double)m->npad * (8 + m->ncp), st);
@@ -1145,7 +1147,9 @@ static int predict_few_set(emub_emulator *const *emus, int nr, cudaStream_t st, 
 	}
 	{
 		LaunchScope ls(c, EMUB_K_GEMM_PRED, (double)m->npad * m->npad * 8 * nr, st);
-		k_few_wk<<<dim3(m->npad / 32, nsplit, nr), 256, 0, st>>>(nullptr, m->npad, w->dK, ldk, w->dFew, m->npad, w->dFewSet, TB, tstride);
+		const dim3 grid(m->npad / 32, nsplit, nr);
+		if (mq == 1) k_few_wk<1><<<grid, 256, 0, st>>>(nullptr, m->npad, w->dK, ldk, w->dFew, m->npad, w->dFewSet, TB, tstride);
+		else k_few_wk<8><<<grid, 256, 0, st>>>(nullptr, m->npad, w->dK, ldk, w->dFew, m->npad, w->dFewSet, TB, tstride);
 	}
 	{
 		LaunchScope ls(c, EMUB_K_SKINNY, 8.0 * (double)m->npad * (8 + m->ncp) * nr, st);

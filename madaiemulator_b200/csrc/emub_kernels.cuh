@@ -719,12 +719,15 @@ __global__ void __launch_bounds__(128) k_pred_final(const double *__restrict__ Q
 constexpr int FEW_MAX = 8;      // query points per call on this path
 constexpr int FEW_JC = 512;     // columns of W per partial product
 
-// T[js][i][0..8) = sum_{j in chunk js, j <= i} W[i][j] K[j][0..8)     grid (npad/32, ceil(npad/FEW_JC)), 256 threads
+// T[js][i][0..NCOL) = sum_{j in chunk js, j <= i} W[i][j] K[j][0..NCOL)     grid (npad/32, ceil(npad/FEW_JC)), 256 threads
+// NCOL = 8, or 1 for the single query point of an MCMC step: few registers, so twice the loads in flight.
 // set != null: component z = blockIdx.z uses set[z].W, the columns [z * kstride, ..) of K and T + z * tstride
+template <int NCOL>
 __global__ void __launch_bounds__(256) k_few_wk(const double *__restrict__ W, int ld, const double *__restrict__ K, int ldk,
                                                 double *__restrict__ T, int npad, const FewSet *__restrict__ set, int kstride,
                                                 long long tstride)
 {
+	constexpr int UNROLL = (NCOL == 1) ? 8 : 4;
 	if (set) {
 		W = set[blockIdx.z].W;
 		K += (size_t)blockIdx.z * kstride;
@@ -735,38 +738,42 @@ __global__ void __launch_bounds__(256) k_few_wk(const double *__restrict__ W, in
 	const int r0 = blockIdx.x * 32 + warp * 4;
 	if (j_lo > r0 + 3) return;  // the chunk lies right of the diagonal for these rows
 	const int jend = min(j_lo + FEW_JC - 1, r0 + 3);
-	double acc[4][8];
+	double acc[4][NCOL];
 #pragma unroll
 	for (int r = 0; r < 4; r++)
 #pragma unroll
-		for (int c = 0; c < 8; c++) acc[r][c] = 0.0;
-	// four steps of 32 columns at a time, every load of the group issued before the first use (the loop bound is not
-	// a compile-time constant, so the compiler would not overlap the iterations on its own)
-	for (int jb = j_lo + lane; jb <= jend; jb += 128) {
-		double wv[4][4];
-		double4 v0[4], v1[4];
+		for (int c = 0; c < NCOL; c++) acc[r][c] = 0.0;
+	// UNROLL steps of 32 columns at a time, every load of the group issued before the first use (the loop bound is
+	// not a compile-time constant, so the compiler would not overlap the iterations on its own)
+	for (int jb = j_lo + lane; jb <= jend; jb += 32 * UNROLL) {
+		double wv[UNROLL][4];
+		double v[UNROLL][NCOL];
 #pragma unroll
-		for (int u = 0; u < 4; u++) {
+		for (int u = 0; u < UNROLL; u++) {
 			const int j = jb + 32 * u;
 			const bool in = j <= jend;
 #pragma unroll
 			for (int r = 0; r < 4; r++) wv[u][r] = (in && j <= r0 + r) ? W[(size_t)(r0 + r) * ld + j] : 0.0;
-			v0[u] = in ? *reinterpret_cast<const double4 *>(K + (size_t)j * ldk) : make_double4(0.0, 0.0, 0.0, 0.0);
-			v1[u] = in ? *reinterpret_cast<const double4 *>(K + (size_t)j * ldk + 4) : make_double4(0.0, 0.0, 0.0, 0.0);
+			if (NCOL == 1) v[u][0] = in ? K[(size_t)j * ldk] : 0.0;
+			else {
+#pragma unroll
+				for (int c = 0; c < NCOL; c += 4) {
+					const double4 t = in ? *reinterpret_cast<const double4 *>(K + (size_t)j * ldk + c) : make_double4(0.0, 0.0, 0.0, 0.0);
+					v[u][c] = t.x; v[u][c + 1] = t.y; v[u][c + 2] = t.z; v[u][c + 3] = t.w;
+				}
+			}
 		}
 #pragma unroll
-		for (int u = 0; u < 4; u++)
+		for (int u = 0; u < UNROLL; u++)
 #pragma unroll
-			for (int r = 0; r < 4; r++) {
-				const double w = wv[u][r];
-				acc[r][0] += w * v0[u].x; acc[r][1] += w * v0[u].y; acc[r][2] += w * v0[u].z; acc[r][3] += w * v0[u].w;
-				acc[r][4] += w * v1[u].x; acc[r][5] += w * v1[u].y; acc[r][6] += w * v1[u].z; acc[r][7] += w * v1[u].w;
-			}
+			for (int r = 0; r < 4; r++)
+#pragma unroll
+				for (int c = 0; c < NCOL; c++) acc[r][c] += wv[u][r] * v[u][c];
 	}
 #pragma unroll
 	for (int r = 0; r < 4; r++)
 #pragma unroll
-		for (int c = 0; c < 8; c++) {
+		for (int c = 0; c < NCOL; c++) {
 			double s = acc[r][c];
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -776,9 +783,12 @@ __global__ void __launch_bounds__(256) k_few_wk(const double *__restrict__ W, in
 		double *o = T + ((size_t)js * npad + r0 + lane) * 8;
 #pragma unroll
 		for (int r = 0; r < 4; r++)
-			if (lane == r)
+			if (lane == r) {
 #pragma unroll
-				for (int c = 0; c < 8; c++) o[c] = acc[r][c];
+				for (int c = 0; c < NCOL; c++) o[c] = acc[r][c];
+#pragma unroll
+				for (int c = NCOL; c < 8; c++) o[c] = 0.0;
+			}
 	}
 }
 
