@@ -18,6 +18,7 @@
 // Slots are processed in lock step per stream group, groups run concurrently on their own streams.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -148,7 +149,9 @@ struct emub_emulator {
 	double *W, *AB, *beta, *Minv, *consts;
 	double kappa;
 	double hbeta[MAXNCP];
+	unsigned long long uid;  // never reused: device addresses are, so caches of emulator sets key on this
 };
+static std::atomic<unsigned long long> g_emulator_uid{1};
 
 extern "C" const char *emub_last_error(void) { return g_err; }
 extern "C" const char *emub_version(void) { return "emub 0.1 (sm_100a, FP64 DMMA)"; }
@@ -998,6 +1001,7 @@ extern "C" int emub_emulator_create_comp(emub_model *m, int comp, const double *
 	memset(e, 0, sizeof(*e));
 	e->m = m;
 	e->kappa = hc[0] + hc[1];  // c(x*, x*) = amp + nugget   (emulator_struct.c:135)
+	e->uid = g_emulator_uid.fetch_add(1);
 	for (int i = 0; i < m->p; i++) e->hbeta[i] = m->hRes[RES_BETA + i];
 	const size_t sUG = (size_t)m->npad * m->ncp;
 	if (cudaMalloc(&e->W, m->mat * sizeof(double)) != cudaSuccess || cudaMalloc(&e->AB, sUG * sizeof(double)) != cudaSuccess ||
@@ -1106,13 +1110,7 @@ static int predict_few_set(emub_emulator *const *emus, int nr, cudaStream_t st, 
 	std::vector<FewSet> hs((size_t)nr);
 	for (int j = 0; j < nr; j++) {
 		hs[j] = FewSet{emus[j]->W, emus[j]->AB, emus[j]->beta, emus[j]->Minv, emus[j]->kappa};
-		const unsigned long long words[6] = {(unsigned long long)(uintptr_t)emus[j]->W, (unsigned long long)(uintptr_t)emus[j]->AB,
-		                                     (unsigned long long)(uintptr_t)emus[j]->beta, (unsigned long long)(uintptr_t)emus[j]->Minv,
-		                                     (unsigned long long)(uintptr_t)emus[j]->consts, 0};
-		for (int k = 0; k < 5; k++) h = (h ^ words[k]) * 1099511628211ull;
-		unsigned long long bits;
-		memcpy(&bits, &emus[j]->kappa, sizeof(bits));
-		h = (h ^ bits) * 1099511628211ull;
+		h = (h ^ emus[j]->uid) * 1099511628211ull;
 	}
 	if (h == 0) h = 1;
 	if (h != w->few_hash) {

@@ -116,6 +116,17 @@ def test_predict_multi_many_observables(ctx):
     assert np.max(np.abs(mf - mean[:3])) < 1e-11 * max(1.0, np.max(np.abs(mean))) and np.max(np.abs(vf - var[:3])) < 1e-11 * max(1.0, np.max(np.abs(var)))
     mf, vf = engine.predict_multi(emus, pts[:1], few=True)
     assert np.max(np.abs(mf - mp[:1])) < 1e-11 and np.max(np.abs(vf - vp[:1])) < 1e-11
+    # emulators rebuilt with other length scales (same amplitude and nugget, very likely the same device addresses):
+    # the cached table of the few-points path must not survive them
+    for e in emus:
+        e.close()
+    thetas2 = thetas.copy()
+    thetas2[:, 2:] += 0.4
+    emus = [m.emulator(thetas2[c], comp=c) for c in range(nr)]
+    mb2, vb2 = engine.predict_multi(emus, pts[:2])
+    mf2, vf2 = engine.predict_multi(emus, pts[:2], few=True)
+    assert np.max(np.abs(mf2 - mb2)) < 1e-11 and np.max(np.abs(vf2 - vb2)) < 1e-11
+    assert np.max(np.abs(mb2 - mp[:2])) > 1e-6  # and they really are different emulators
     with pytest.raises(engine.EmubError):
         engine.predict_multi(emus, pts, np.zeros(2000), np.zeros((2000, nr)), lam)
     for e in emus:
