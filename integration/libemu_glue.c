@@ -38,6 +38,9 @@
 #define GLUE_MAX 256
 
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+/* the reference's emulate_point is re-entrant (emulator_struct.c:124-143 touches only its arguments); an engine
+ * context serves one call at a time, so concurrent callers take turns here */
+static pthread_mutex_t g_call_mu = PTHREAD_MUTEX_INITIALIZER;
 static emub_ctx *g_ctx = NULL;
 static struct { const void *key_x, *key_y; int n, d, kernel, order; unsigned long long hash; emub_model *m; } g_models[GLUE_MAX];
 static int g_nmodels = 0;
@@ -270,7 +273,10 @@ void emulate_point(emulator_struct *e, gsl_vector *point, double *mean, double *
 	emub_emulator *eh = glue_emulator_for(e, 0);
 	double x[64];
 	for (int i = 0; i < e->nparams; i++) x[i] = gsl_vector_get(point, i);
-	if (!eh || emub_predict_few(eh, x, e->nparams, 1, mean, variance) != EMUB_OK) glue_die("emub_predict_few");
+	pthread_mutex_lock(&g_call_mu);
+	const int rc = eh ? emub_predict_few(eh, x, e->nparams, 1, mean, variance) : EMUB_EINVAL;
+	pthread_mutex_unlock(&g_call_mu);
+	if (rc != EMUB_OK) glue_die("emub_predict_few");
 }
 
 /* emulate-fns.c:73 -- covariance, factorisation and regression once, then every point of the list: one emulator, one

@@ -217,7 +217,12 @@ static void mv_emulate(multi_emulator *emu, gsl_vector *the_point, gsl_vector *t
 	const int d = emu->nparams, nt = emu->nt, nout = pca ? emu->nr : emu->nt;
 	if (d > 64 || nt > 4096) { fprintf(stderr, "multivar_glue: model too wide\n"); exit(EXIT_FAILURE); }
 	for (int k = 0; k < d; k++) pt[k] = gsl_vector_get(the_point, k);
-	if (emub_multi_emulator_predict_few(me, pt, 1, pca, mean, var) != EMUB_OK) mv_die("emulate_point_multi");
+	/* the reference's emulate_point_multi is re-entrant; an engine context serves one call at a time */
+	static pthread_mutex_t call_mu = PTHREAD_MUTEX_INITIALIZER;
+	pthread_mutex_lock(&call_mu);
+	const int rc = emub_multi_emulator_predict_few(me, pt, 1, pca, mean, var);
+	pthread_mutex_unlock(&call_mu);
+	if (rc != EMUB_OK) mv_die("emulate_point_multi");
 	for (int i = 0; i < nout; i++) {
 		gsl_vector_set(the_mean, i, mean[i]);
 		gsl_vector_set(the_variance, i, var[i]);
