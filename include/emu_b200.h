@@ -116,7 +116,7 @@ int emub_emulator_beta(emub_emulator *e, double *beta); /* p values */
 int emub_predict_batch(emub_emulator *e, const double *pts, int ldp, int mq, double *mean, double *var);
 /* emulate_point for a handful of points (mq <= 8) -- the call pattern of an MCMC driver (EmuPlusPlus::QueryEmulator,
  * EmuPlusPlus.cpp:137-179): a latency path that streams the cached factor once instead of running the batched tensor
- * pass on a 128-column block (n = 4096: 340 -> 78 us per call for one point).  Same quantities as emub_predict_batch; the
+ * pass on a 128-column block (n = 4096: 340 -> 70 us per call for one point).  Same quantities as emub_predict_batch; the
  * sums run in another order, so the two agree to rounding (1e-15), not bit for bit. */
 int emub_predict_few(emub_emulator *e, const double *pts, int ldp, int mq, double *mean, double *var);
 /* emulate_point_multi (multivar_support.c:103-157) for mq points: all nr PCA components (emulators of one model) and

@@ -133,6 +133,10 @@ struct QueryWs {
 	double *dFewConsts;                           // [few_cap][CONST_STRIDE], contiguous copy of the emulators' constants
 	int few_cap;                                  // emulators dFewSet / dFewConsts / dFew hold
 	unsigned long long few_hash;                  // which emulators the tables describe (0: none)
+	// the few-points call sequences (copy in, 4-5 kernels, copies out) replayed as CUDA graphs; every pointer in them
+	// belongs to this workspace or to the emulators named by the key
+	struct { unsigned long long key; cudaGraphExec_t exec; long long launches; } few_graphs[8];
+	int few_graph_next;
 	double *dOutM, *dOutV, *dProj;                // back-projected outputs (mqc x ntmax), projection data
 	GemmTask *dTasks;
 	double *hQ, *hOut;  // pinned
@@ -405,10 +409,20 @@ extern "C" int emub_model_nthetas(const emub_model *m) { return m ? m->nth : 0; 
 extern "C" int emub_model_nregression_fns(const emub_model *m) { return m ? m->p : 0; }
 extern "C" int emub_model_slots(const emub_model *m) { return m ? m->nslots : 0; }
 
+static void few_graphs_clear(QueryWs *w)
+{
+	for (auto &g : w->few_graphs) {
+		if (g.exec) cudaGraphExecDestroy(g.exec);
+		g.exec = nullptr;
+		g.key = 0;
+	}
+}
+
 static void free_query_ws(emub_model *m)
 {
 	QueryWs *w = m->qws;
 	if (!w) return;
+	few_graphs_clear(w);
 	cudaFree(w->dQ); cudaFree(w->dK); cudaFree(w->dVsq); cudaFree(w->dKA); cudaFree(w->dMean); cudaFree(w->dVar);
 	cudaFree(w->dOutM); cudaFree(w->dOutV); cudaFree(w->dProj); cudaFree(w->dTasks); cudaFree(w->dFew);
 	cudaFree(w->dFewSet); cudaFree(w->dFewConsts);
@@ -958,6 +972,7 @@ static int ensure_output_capacity(emub_model *m, int need)
 	cudaFreeHost(w->hOutb[0]); cudaFreeHost(w->hOutb[1]);
 	w->dOutM = w->dOutV = w->dProj = nullptr;
 	w->proj_hash = 0;
+	few_graphs_clear(w);
 	w->hOut = w->hOutb[0] = w->hOutb[1] = nullptr;
 	w->ntcap = 0;
 	CUDA_TRY(cudaMalloc(&w->dOutM, sizeof(double) * (size_t)cap * w->mqc));
@@ -1097,15 +1112,14 @@ static bool few_set_fits(const emub_model *m, int nr)
 	return (long long)nr * TB <= w->mqc && (long long)nr * nparts * FEW_MAX <= w->mqc;
 }
 
-static int predict_few_set(emub_emulator *const *emus, int nr, cudaStream_t st, const double *dQ, int mq, double *dMean, double *dVar)
+// tables of the set (device buffers of every emulator, a contiguous copy of their constants): rebuilt when the set
+// changes; *hash_out identifies the set
+static int few_set_prepare(emub_emulator *const *emus, int nr, cudaStream_t st, unsigned long long *hash_out)
 {
 	emub_model *m = emus[0]->m;
-	emub_ctx *c = m->ctx;
 	QueryWs *w = m->qws;
-	const int ldk = w->mqc;
-	const int nsplit = (m->npad + FEW_JC - 1) / FEW_JC, nparts = m->npad / FEW_ROWS;
-	const long long tstride = (long long)nsplit * m->npad * 8, kastride = (long long)nparts * FEW_MAX * m->ncp;
-	// tables: rebuilt when the set of emulators (their device buffers) changes
+	const int nsplit = (m->npad + FEW_JC - 1) / FEW_JC;
+	const long long tstride = (long long)nsplit * m->npad * 8;
 	unsigned long long h = 1469598103934665603ull ^ (unsigned long long)nr;
 	std::vector<FewSet> hs((size_t)nr);
 	for (int j = 0; j < nr; j++) {
@@ -1117,6 +1131,7 @@ static int predict_few_set(emub_emulator *const *emus, int nr, cudaStream_t st, 
 		w->few_hash = 0;
 		if (nr > w->few_cap || !w->dFewSet) {
 			CUDA_TRY(cudaStreamSynchronize(st));
+			few_graphs_clear(w);
 			cudaFree(w->dFewSet); cudaFree(w->dFewConsts); cudaFree(w->dFew);
 			w->dFewSet = nullptr; w->dFewConsts = nullptr; w->dFew = nullptr;
 			w->few_cap = 0;
@@ -1132,6 +1147,19 @@ static int predict_few_set(emub_emulator *const *emus, int nr, cudaStream_t st, 
 		CUDA_TRY(cudaStreamSynchronize(st));  // hs is a local
 		w->few_hash = h;
 	}
+	*hash_out = h;
+	return EMUB_OK;
+}
+
+// the kernels of the set path (capturable: no synchronisation, no host data)
+static int few_set_launch(emub_emulator *const *emus, int nr, cudaStream_t st, const double *dQ, int mq, double *dMean, double *dVar)
+{
+	emub_model *m = emus[0]->m;
+	emub_ctx *c = m->ctx;
+	QueryWs *w = m->qws;
+	const int ldk = w->mqc;
+	const int nsplit = (m->npad + FEW_JC - 1) / FEW_JC, nparts = m->npad / FEW_ROWS;
+	const long long tstride = (long long)nsplit * m->npad * 8, kastride = (long long)nparts * FEW_MAX * m->ncp;
 	{
 		// cross covariances of every component: component z at the columns [128 z, 128 z + 128) of dK
 		const size_t smem = 2 * (size_t)m->d * CT * sizeof(double);
@@ -1247,6 +1275,58 @@ extern "C" int emub_predict_batch(emub_emulator *e, const double *pts, int ldp, 
 
 // emulate_point for a handful of points (mq <= 8), the call pattern of an MCMC driver: no chunk walk, the skinny
 // latency path of predict_chunk
+// Runs `enqueue` (copies and kernels on st, nothing else) -- as a replayed CUDA graph when graphs are on: one launch per
+// call instead of six to eight.  key must change whenever any pointer or size inside the sequence does.
+template <class Enqueue>
+static int few_run(emub_model *m, unsigned long long key, cudaStream_t st, Enqueue enqueue)
+{
+	emub_ctx *c = m->ctx;
+	QueryWs *w = m->qws;
+	if (c->profile || !c->use_graphs) {
+		int rc = enqueue();
+		if (rc) return rc;
+		CUDA_TRY(cudaStreamSynchronize(st));
+		return EMUB_OK;
+	}
+	if (key == 0) key = 1;
+	int slot = -1;
+	for (int i = 0; i < 8; i++)
+		if (w->few_graphs[i].key == key && w->few_graphs[i].exec) slot = i;
+	if (slot < 0) {
+		slot = w->few_graph_next;
+		w->few_graph_next = (w->few_graph_next + 1) % 8;
+		if (w->few_graphs[slot].exec) { cudaGraphExecDestroy(w->few_graphs[slot].exec); w->few_graphs[slot].exec = nullptr; }
+		w->few_graphs[slot].key = 0;
+		const long long before = c->launches;
+		cudaGraph_t graph = nullptr;
+		CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+		int rc = enqueue();
+		cudaError_t ce = cudaStreamEndCapture(st, &graph);
+		if (rc != EMUB_OK || ce != cudaSuccess || !graph) {
+			if (graph) cudaGraphDestroy(graph);
+			cudaGetLastError();
+			return rc != EMUB_OK ? rc : set_err(EMUB_ECUDA, "CUDA graph capture failed: %s", cudaGetErrorString(ce));
+		}
+		ce = cudaGraphInstantiate(&w->few_graphs[slot].exec, graph, 0);
+		cudaGraphDestroy(graph);
+		if (ce != cudaSuccess) { w->few_graphs[slot].exec = nullptr; return set_err(EMUB_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+		w->few_graphs[slot].key = key;
+		w->few_graphs[slot].launches = c->launches - before;
+		c->launches = before;
+	}
+	c->launches += w->few_graphs[slot].launches;
+	CUDA_TRY(cudaGraphLaunch(w->few_graphs[slot].exec, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	return EMUB_OK;
+}
+
+static unsigned long long few_key(unsigned long long h, unsigned long long a, unsigned long long b, unsigned long long c2)
+{
+	const unsigned long long words[3] = {a, b, c2};
+	for (unsigned long long v : words) h = (h ^ v) * 1099511628211ull;
+	return h;
+}
+
 extern "C" int emub_predict_few(emub_emulator *e, const double *pts, int ldp, int mq, double *mean, double *var)
 {
 	if (!e || !pts || !mean || !var || mq < 0 || mq > FEW_MAX || ldp < e->m->d) return set_err(EMUB_EINVAL, "emub_predict_few: bad argument (at most 8 points)%s");
@@ -1257,13 +1337,16 @@ extern "C" int emub_predict_few(emub_emulator *e, const double *pts, int ldp, in
 	QueryWs *w = m->qws;
 	cudaStream_t st = m->ctx->streams[0];
 	for (int q = 0; q < mq; q++) memcpy(w->hQ + (size_t)q * m->d, pts + (size_t)q * ldp, sizeof(double) * m->d);
-	CUDA_TRY(cudaMemcpyAsync(w->dQ, w->hQ, sizeof(double) * (size_t)mq * m->d, cudaMemcpyHostToDevice, st));
-	int rc = predict_chunk(e, st, w->dQ, mq, w->dMean, w->dVar, true);
+	int rc = few_run(m, few_key(1469598103934665603ull, e->uid, (unsigned long long)mq, 0x53ull), st, [&]() -> int {
+		CUDA_TRY(cudaMemcpyAsync(w->dQ, w->hQ, sizeof(double) * (size_t)mq * m->d, cudaMemcpyHostToDevice, st));
+		int r = predict_chunk(e, st, w->dQ, mq, w->dMean, w->dVar, true);
+		if (r) return r;
+		// mean and variance sit mqc apart: one copy of the first FEW_MAX of each
+		CUDA_TRY(cudaMemcpyAsync(w->hOut, w->dMean, sizeof(double) * mq, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaMemcpyAsync(w->hOut + FEW_MAX, w->dVar, sizeof(double) * mq, cudaMemcpyDeviceToHost, st));
+		return EMUB_OK;
+	});
 	if (rc) return rc;
-	// mean and variance sit mqc apart: one copy of the first FEW_MAX of each
-	CUDA_TRY(cudaMemcpyAsync(w->hOut, w->dMean, sizeof(double) * mq, cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaMemcpyAsync(w->hOut + FEW_MAX, w->dVar, sizeof(double) * mq, cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaStreamSynchronize(st));
 	memcpy(mean, w->hOut, sizeof(double) * mq);
 	memcpy(var, w->hOut + FEW_MAX, sizeof(double) * mq);
 	return EMUB_OK;
@@ -1329,42 +1412,62 @@ static int predict_multi_impl(emub_emulator *const *emus, int nr, const double *
 		}
 	}
 	const size_t vofs = (size_t)w->ntcap * w->mqc;  // variances start here in a host output buffer
-	return walk_query_chunks(
-	    m, pts, ldp, mq,
-	    [&](int cnt, const double *dQ, double *hOut) -> int {
-		    if (few && nr > 1 && cnt <= FEW_MAX && few_set_fits(m, nr)) {
-			    int rc = predict_few_set(emus, nr, st, dQ, cnt, w->dMean, w->dVar);
-			    if (rc) return rc;
-		    } else {
-			    for (int j = 0; j < nr; j++) {
-				    int rc = predict_chunk(emus[j], st, dQ, cnt, w->dMean + (size_t)j * w->mqc, w->dVar + (size_t)j * w->mqc, few);
-				    if (rc) return rc;
-			    }
-		    }
-		    if (nt > 0) {
-			    {
-				    LaunchScope ls(m->ctx, EMUB_K_PRED_FINAL, 0, st);
-				    k_backproject<<<(cnt + 127) / 128, 128, 0, st>>>(w->dMean, w->dVar, w->mqc, cnt, nt, nr, w->dProj, w->dProj + nt,
-				                                                     w->dProj + nt + (size_t)nt * nr, w->dOutM, w->dOutV);
-			    }
-			    CUDA_TRY(cudaMemcpyAsync(hOut, w->dOutM, sizeof(double) * (size_t)cnt * nt, cudaMemcpyDeviceToHost, st));
-			    CUDA_TRY(cudaMemcpyAsync(hOut + vofs, w->dOutV, sizeof(double) * (size_t)cnt * nt, cudaMemcpyDeviceToHost, st));
-		    } else {
-			    CUDA_TRY(cudaMemcpy2DAsync(hOut, sizeof(double) * cnt, w->dMean, sizeof(double) * w->mqc, sizeof(double) * cnt, nr, cudaMemcpyDeviceToHost, st));
-			    CUDA_TRY(cudaMemcpy2DAsync(hOut + vofs, sizeof(double) * cnt, w->dVar, sizeof(double) * w->mqc, sizeof(double) * cnt, nr, cudaMemcpyDeviceToHost, st));
-		    }
-		    return EMUB_OK;
-	    },
-	    [&](int done, int cnt, const double *hOut) {
-		    if (nt > 0) {
-			    memcpy(mean + (size_t)done * nt, hOut, sizeof(double) * (size_t)cnt * nt);
-			    memcpy(var + (size_t)done * nt, hOut + vofs, sizeof(double) * (size_t)cnt * nt);
-		    } else {
-			    for (int q = 0; q < cnt; q++)
-				    for (int j = 0; j < nr; j++) {
-					    mean[(size_t)(done + q) * nr + j] = hOut[(size_t)j * cnt + q];
-					    var[(size_t)(done + q) * nr + j] = hOut[vofs + (size_t)j * cnt + q];
-				    }
-		    }
-	    });
+	const bool few_set = few && nr > 1 && mq <= FEW_MAX && few_set_fits(m, nr);
+	auto compute = [&](int cnt, const double *dQ, double *hOut) -> int {
+		if (few_set) {  // tables prepared by the caller of this lambda
+			int rc = few_set_launch(emus, nr, st, dQ, cnt, w->dMean, w->dVar);
+			if (rc) return rc;
+		} else {
+			for (int j = 0; j < nr; j++) {
+				int rc = predict_chunk(emus[j], st, dQ, cnt, w->dMean + (size_t)j * w->mqc, w->dVar + (size_t)j * w->mqc, few);
+				if (rc) return rc;
+			}
+		}
+		if (nt > 0) {
+			{
+				LaunchScope ls(m->ctx, EMUB_K_PRED_FINAL, 0, st);
+				k_backproject<<<(cnt + 127) / 128, 128, 0, st>>>(w->dMean, w->dVar, w->mqc, cnt, nt, nr, w->dProj, w->dProj + nt,
+				                                                 w->dProj + nt + (size_t)nt * nr, w->dOutM, w->dOutV);
+			}
+			CUDA_TRY(cudaMemcpyAsync(hOut, w->dOutM, sizeof(double) * (size_t)cnt * nt, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpyAsync(hOut + vofs, w->dOutV, sizeof(double) * (size_t)cnt * nt, cudaMemcpyDeviceToHost, st));
+		} else {
+			CUDA_TRY(cudaMemcpy2DAsync(hOut, sizeof(double) * cnt, w->dMean, sizeof(double) * w->mqc, sizeof(double) * cnt, nr, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpy2DAsync(hOut + vofs, sizeof(double) * cnt, w->dVar, sizeof(double) * w->mqc, sizeof(double) * cnt, nr, cudaMemcpyDeviceToHost, st));
+		}
+		return EMUB_OK;
+	};
+	auto collect = [&](int done, int cnt, const double *hOut) {
+		if (nt > 0) {
+			memcpy(mean + (size_t)done * nt, hOut, sizeof(double) * (size_t)cnt * nt);
+			memcpy(var + (size_t)done * nt, hOut + vofs, sizeof(double) * (size_t)cnt * nt);
+		} else {
+			for (int q = 0; q < cnt; q++)
+				for (int j = 0; j < nr; j++) {
+					mean[(size_t)(done + q) * nr + j] = hOut[(size_t)j * cnt + q];
+					var[(size_t)(done + q) * nr + j] = hOut[vofs + (size_t)j * cnt + q];
+				}
+		}
+	};
+	if (few) {
+		// a handful of points: no chunk walk; the whole sequence (copy in, kernels, copies out) is one replayed graph
+		if (mq == 0) return EMUB_OK;
+		unsigned long long hset = 1469598103934665603ull;
+		if (few_set) {
+			int rc = few_set_prepare(emus, nr, st, &hset);
+			if (rc) return rc;
+		} else
+			for (int j = 0; j < nr; j++) hset = (hset ^ emus[j]->uid) * 1099511628211ull;
+		for (int q = 0; q < mq; q++) memcpy(w->hQ + (size_t)q * m->d, pts + (size_t)q * ldp, sizeof(double) * m->d);
+		const unsigned long long shape = (unsigned long long)mq | ((unsigned long long)nt << 8) | ((unsigned long long)nr << 24) |
+		                                 ((unsigned long long)few_set << 40);
+		int rc = few_run(m, few_key(hset, shape, nt > 0 ? w->proj_hash : 0, 0x4Dull), st, [&]() -> int {
+			CUDA_TRY(cudaMemcpyAsync(w->dQ, w->hQ, sizeof(double) * (size_t)mq * m->d, cudaMemcpyHostToDevice, st));
+			return compute(mq, w->dQ, w->hOut);
+		});
+		if (rc) return rc;
+		collect(0, mq, w->hOut);
+		return EMUB_OK;
+	}
+	return walk_query_chunks(m, pts, ldp, mq, compute, collect);
 }
