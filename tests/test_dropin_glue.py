@@ -196,6 +196,19 @@ def test_reference_cli_interactive_mode_with_batched_front_doors(flag, golden, n
     _compare_protocol(out, os.path.join(cdir, golden), 6, 0 if flag else 1 + 3 + 1 + 12, nr)
 
 
+def test_reference_cli_single_output_model_with_batched_front_doors():
+    """a one-output model (nt = nr = 1, BASELINE config 0): the few-points path without the component table"""
+    import os
+    import subprocess
+    from tests.test_interactive_stream import _compare_protocol
+    root, cli = _multi_bin("interactive_emulator_dropin_multi")
+    cdir = os.path.join(root, "tests", "golden", "cli")
+    inp = open(os.path.join(cdir, "uni-simple.points"), "rb").read()
+    out = subprocess.run([cli, "interactive_mode", os.path.join(cdir, "uni-simple-o1.snapshot")], input=inp, capture_output=True,
+                         check=True, timeout=300).stdout.decode()
+    _compare_protocol(out, os.path.join(cdir, "uni-simple-o1.interactive.txt"), 1, 1 + 1 + 1 + 2)
+
+
 def test_emuplusplus_with_batched_front_doors():
     import os
     import subprocess
