@@ -49,3 +49,33 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".c", ".h", ".cu", ".cuh", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in txt and "emu_oracle" not in txt and "libemu_ref" not in txt, f
+
+
+def test_glue_libraries_define_the_reference_symbols():
+    """The drop-in builds (reference objects + integration/*.c) export the reference's own names, and the glue's
+    definitions -- not the weakened reference ones -- are what a caller binds to: they live in the glue's address
+    range, i.e. next to a glue-only helper symbol."""
+    import subprocess
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    base = os.path.join(ref_dir, "libemu_dropin.so")
+    multi = os.path.join(ref_dir, "libemu_dropin_multi.so")
+    if not (os.path.exists(base) and os.path.exists(multi)):
+        pytest.skip("oracle/_ref drop-in builds not present")
+
+    def defined(lib):
+        out = subprocess.check_output(["nm", "-D", "--defined-only", lib]).decode().split("\n")
+        return {ln.split()[2]: ln.split()[1] for ln in out if len(ln.split()) == 3}
+
+    hot = ["evalFnMulti", "gradFnMulti", "evalFnGradMulti", "estimateSigmaFull", "estimate_thetas_threaded", "alloc_emulator_struct",
+           "free_emulator_struct", "emulate_point", "makeCovMatrix_fnptr", "emulateAtPointList", "emulateAtPoint"]
+    mv = ["estimate_multi", "alloc_multi_emulator", "free_multi_emulator", "emulate_point_multi", "emulate_point_multi_pca"]
+    b, m = defined(base), defined(multi)
+    for name in hot:
+        assert b.get(name) == "T" and m.get(name) == "T", name  # strong definitions (the reference's are weakened to W)
+    for name in mv:
+        assert m.get(name) == "T", name
+    assert "libemu_glue_reset" in b and "libemu_glue_reset" in m
+    # the integration sources never include a CPU implementation of the path
+    for f in ("libemu_glue.c", "multivar_glue.c", "rbind_glue.c"):
+        txt = open(os.path.join(ROOT, "integration", f)).read()
+        assert "gsl_linalg_cholesky" not in txt and "emu_oracle" not in txt
