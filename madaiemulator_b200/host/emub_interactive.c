@@ -1,6 +1,7 @@
 /* emub_interactive.c -- see emub_interactive.h.  Citations are file:line under the reference's src/. */
 #define _GNU_SOURCE
 #include "emub_interactive.h"
+#include "emub_fastfloat.h"
 #include <fcntl.h>
 #include <poll.h>
 #include <pthread.h>
@@ -264,9 +265,12 @@ static void parse_convert(void *arg, int s)
 		if (p >= end) break;
 		char *q = p;
 		while (q < end && !is_sep(*q)) q++;
-		char *stop;
-		const double v = strtod(p, &stop);
-		if (stop == p) { j->bad[s] = g; break; } /* not a number: the reference's fscanf stops here too */
+		double v;
+		if (!emub_fast_strtod(p, q, &v)) { /* plain decimal tokens take the exact fast conversion, the rest strtod */
+			char *stop;
+			v = strtod(p, &stop);
+			if (stop == p) { j->bad[s] = g; break; } /* not a number: the reference's fscanf stops here too */
+		}
 		j->out[g++] = v;
 		p = q;
 	}

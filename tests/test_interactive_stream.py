@@ -173,6 +173,37 @@ def test_parallel_text_parser():
             assert np.array_equal(got.view(np.uint64), expect[:cap].view(np.uint64))
             rest, c2, _ = _parse(H, text[consumed:], len(toks), threads)
             assert np.array_equal(rest.view(np.uint64), expect[cap:].view(np.uint64))
+    # the exact fast conversion (Eisel-Lemire) behind the parser, against Python's correctly rounded float() on shapes
+    # that stress it: 1-19 digit significands with exponents over the whole range, ties above 2^53, subnormals,
+    # overflow, more than 19 digits, leading zeros, signs
+    toks2 = []
+    for i in range(120000):
+        kind = i % 8
+        if kind == 0:
+            toks2.append("%de%d" % (rng.integers(1, 2 ** 63), rng.integers(-345, 330)))
+        elif kind == 1:
+            toks2.append("%d" % (2 ** 53 + 2 * int(rng.integers(0, 4096)) + 1))
+        elif kind == 2:
+            toks2.append("%.*e" % (int(rng.integers(0, 19)), rng.uniform(1, 10) * 10.0 ** int(rng.integers(-320, 308))))
+        elif kind == 3:
+            toks2.append("%s0.%s%d" % ("-" if i & 8 else "", "0" * int(rng.integers(0, 30)), rng.integers(1, 2 ** 62)))
+        elif kind == 4:
+            toks2.append(repr(float(np.float64(rng.integers(1, 2 ** 62)).view(np.float64)) if False else float(rng.standard_cauchy())))
+        elif kind == 5:
+            toks2.append("%d.%d" % (rng.integers(0, 10 ** 6), rng.integers(0, 10 ** 13)))
+        elif kind == 6:
+            toks2.append("%d%d" % (rng.integers(1, 2 ** 62), rng.integers(1, 2 ** 62)))  # > 19 digits: strtod path
+        else:
+            toks2.append("%.17g" % (float(np.frombuffer(rng.bytes(8), dtype=np.uint64)[0] % (2 ** 62)) * 4.9e-324))
+    toks2 += ["1e400", "-1e400", "1e-400", "4.9e-324", "2.2250738585072014e-308", "2.2250738585072011e-308", "1.7976931348623157e308",
+              "9007199254740993", "9007199254740992.5", "0e0", "-0.0", "+1.5", "1.e5", ".5e1", "00012.500", "1E+2"]
+    text2 = (" ".join(toks2) + "\n").encode()
+    expect2 = np.array([float(t) for t in toks2])
+    for threads in (1, 8):
+        got, consumed, bad = _parse(H, text2, len(toks2) + 1, threads)
+        assert bad == 0 and len(got) == len(toks2)
+        diff = np.nonzero(got.view(np.uint64) != expect2.view(np.uint64))[0]
+        assert len(diff) == 0, [(toks2[k], got[k], expect2[k]) for k in diff[:5]]
     # a token that is not a number ends the conversion there (the reference's fscanf stops too)
     broken = b"1.5 2.5\n3.5 oops 4.5\n" + text
     for threads in (1, 8):
