@@ -52,6 +52,19 @@ static int eisel_lemire(uint64_t w, int q, int neg, double *out)
 	return 1;
 }
 
+/* eight ASCII digits at p -> their value (SWAR); 0 if any of the eight bytes is not a digit */
+static inline int eight_digits(const char *p, uint64_t *val)
+{
+	uint64_t v;
+	memcpy(&v, p, 8);
+	if (((v & 0xF0F0F0F0F0F0F0F0ull) | (((v + 0x0606060606060606ull) & 0xF0F0F0F0F0F0F0F0ull) >> 4)) != 0x3333333333333333ull) return 0;
+	v -= 0x3030303030303030ull;
+	v = (v * 10) + (v >> 8);
+	v = (((v & 0x000000FF000000FFull) * 0x000F424000000064ull) + (((v >> 16) & 0x000000FF000000FFull) * 0x0000271000000001ull)) >> 32;
+	*val = v;
+	return 1;
+}
+
 int emub_fast_strtod(const char *p, const char *end, double *out)
 {
 	int neg = 0;
@@ -72,6 +85,14 @@ int emub_fast_strtod(const char *p, const char *end, double *out)
 	if (p < end && *p == '.') {
 		p++;
 		while (p < end && *p >= '0' && *p <= '9') {
+			uint64_t v8;
+			if (w != 0 && nd <= 11 && end - p >= 8 && eight_digits(p, &v8)) { /* every digit is significant from here on */
+				w = w * 100000000ull + v8;
+				nd += 8;
+				frac += 8;
+				p += 8;
+				continue;
+			}
 			if (w != 0 || *p != '0') {
 				if (nd == 19) return 0;
 				w = w * 10 + (uint64_t)(*p - '0');
