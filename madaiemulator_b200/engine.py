@@ -352,7 +352,7 @@ HOST_LIB_PATH = os.path.join(_HERE, "host", "libemuhost.so")
 HOST_SYMBOLS = ["emub_estimate_default_opts", "emub_sample_scales", "emub_optimization_ranges", "emub_random_init",
                 "emub_estimate_thetas", "emub_estimate_thetas_from", "emub_estimate_thetas_multi", "emub_estimate_thetas_multi_devices", "emub_estimate_thetas_multi_devices_ranges", "emub_snapshot_load",
                 "emub_snapshot_load_path", "emub_snapshot_free", "emub_multi_emulator_from_snapshot",
-                "emub_multi_emulator_destroy", "emub_multi_emulator_predict", "emub_multi_emulator_predict_few", "emub_interactive_stream", "emub_parse_doubles",
+                "emub_multi_emulator_destroy", "emub_multi_emulator_predict", "emub_multi_emulator_predict_few", "emub_interactive_stream", "emub_parse_doubles", "emub_fast_strtod", "emub_fast_format17",
                 "emub_snapshot_save", "emub_snapshot_save_path", "emub_snapshot_from_arrays"]
 
 

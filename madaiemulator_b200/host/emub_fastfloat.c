@@ -133,3 +133,65 @@ int emub_fast_strtod(const char *p, const char *end, double *out)
 	}
 	return eisel_lemire(w, (int)q, neg, out);
 }
+
+/* ---- "%.17f\n" ------------------------------------------------------------------------------------------------ */
+static const char k_digit_pairs[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+
+/* exactly ndig decimal digits of v (zero padded) */
+static inline void put_digits(char *b, uint64_t v, int ndig)
+{
+	int i = ndig;
+	while (i >= 2) {
+		const unsigned r = (unsigned)(v % 100);
+		v /= 100;
+		i -= 2;
+		b[i] = k_digit_pairs[2 * r];
+		b[i + 1] = k_digit_pairs[2 * r + 1];
+	}
+	if (i == 1) b[0] = (char)('0' + (int)(v % 10));
+}
+
+int emub_fast_format17(double x, char *buf)
+{
+	uint64_t bits;
+	memcpy(&bits, &x, sizeof(bits));
+	const int neg = (int)(bits >> 63);
+	const int bexp = (int)((bits >> 52) & 0x7FF);
+	uint64_t m = bits & 0x000FFFFFFFFFFFFFull;
+	if (bexp == 0x7FF) return 0;       /* inf, nan */
+	int e;                             /* x = m * 2^e */
+	if (bexp == 0) e = -1074;          /* subnormal (or zero) */
+	else { m |= 1ull << 52; e = bexp - 1075; }
+	if (e > 10) return 0;              /* |x| >= 2^63 */
+	uint64_t ip, q;
+	if (e >= 0) { ip = m << e; q = 0; }
+	else {
+		const int s = -e;              /* 1 .. 1074 */
+		uint64_t fm;
+		if (s < 64) { ip = m >> s; fm = m & ((1ull << s) - 1); }
+		else { ip = 0; fm = m; }
+		if (s >= 128) q = 0;           /* fm * 10^17 < 2^110: rounds to 0 at 17 places */
+		else {
+			const unsigned __int128 P = (unsigned __int128)fm * 100000000000000000ull;
+			const unsigned __int128 one = 1;
+			const unsigned __int128 quo = P >> s, rem = P & ((one << s) - 1), half = one << (s - 1);
+			q = (uint64_t)quo;
+			if (rem > half || (rem == half && (q & 1))) q++;
+			if (q == 100000000000000000ull) { q = 0; ip++; }
+		}
+	}
+	char *b = buf;
+	if (neg) *b++ = '-';
+	/* integer part: up to 19 digits, no leading zeros */
+	char tmp[20];
+	int n = 0;
+	do { tmp[n++] = (char)('0' + (int)(ip % 10)); ip /= 10; } while (ip);
+	while (n) *b++ = tmp[--n];
+	*b++ = '.';
+	put_digits(b, q / 1000000000ull, 8);
+	put_digits(b + 8, q % 1000000000ull, 9);
+	b += 17;
+	*b++ = '\n';
+	return (int)(b - buf);
+}

@@ -11,6 +11,10 @@ extern "C" {
 #endif
 /* converts the whole token [p, end); returns 1 and stores the value, or 0 = declined */
 int emub_fast_strtod(const char *p, const char *end, double *out);
+/* the bytes of printf("%.17f\n", x) (the output format of interactive_mode, interactive_emulator.c:431-437) into buf
+ * (at least 48 bytes); returns their number, or 0 = declined (|x| >= 2^63, inf, nan: use snprintf).  Exact: the
+ * decimal expansion is rounded to 17 places from the full binary value, ties to even, like glibc. */
+int emub_fast_format17(double x, char *buf);
 #ifdef __cplusplus
 }
 #endif

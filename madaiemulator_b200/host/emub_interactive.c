@@ -331,8 +331,12 @@ static void format_part(void *arg, int part)
 				cap = cap * 2 + 4096;
 				b = (char *)realloc(b, cap);
 			}
-			o += (size_t)snprintf(b + o, cap - o, "%.17f\n", j->mean[(size_t)q * j->nt + i]);
-			o += (size_t)snprintf(b + o, cap - o, "%.17f\n", j->var[(size_t)q * j->nt + i]);
+			const double pair[2] = {j->mean[(size_t)q * j->nt + i], j->var[(size_t)q * j->nt + i]};
+			for (int h = 0; h < 2; h++) { /* exact fast formatter, snprintf for what it declines (inf, nan, |x| >= 2^63) */
+				int len = emub_fast_format17(pair[h], b + o);
+				if (len == 0) len = snprintf(b + o, cap - o, "%.17f\n", pair[h]);
+				o += (size_t)len;
+			}
 		}
 	j->buf[part] = b; j->cap[part] = cap; j->len[part] = o;
 }

@@ -216,6 +216,26 @@ def test_parallel_text_parser():
     assert len(got) == 0 and bad == 0
 
 
+def test_fast_formatter_matches_printf():
+    """the output side of the stream: emub_fast_format17 gives the bytes of printf("%.17f\\n") (exact expansion, ties to
+    even) or declines"""
+    from madaiemulator_b200 import engine
+    H = engine.host_lib()
+    H.emub_fast_format17.restype = ctypes.c_int
+    H.emub_fast_format17.argtypes = [ctypes.c_double, ctypes.c_char_p]
+    rng = np.random.default_rng(2)
+    vals = list(rng.uniform(-3, 3, 20000)) + list(rng.normal(size=5000) * 1e-12) + list(rng.normal(size=5000) * 1e12) + \
+        [(2 * int(k) + 1) / 262144.0 for k in rng.integers(0, 10 ** 5, 5000)] + \
+        [0.0, -0.0, 5e-324, -5e-324, 1e-18, 0.5e-17, 1.5e-17, 0.99999999999999999, 9.9999999999999999, 2.0 ** 62, -(2.0 ** 62), 123456789.125,
+         0.000000000000000005, 1.0000000000000002]
+    buf = ctypes.create_string_buffer(64)
+    for v in vals:
+        n = H.emub_fast_format17(float(v), buf)
+        assert n > 0 and buf.raw[:n] == ("%.17f\n" % v).encode(), (v, buf.raw[:n])
+    for v in (float("inf"), float("-inf"), float("nan"), 2.0 ** 63, -1e300):
+        assert H.emub_fast_format17(v, buf) == 0
+
+
 def _compare_protocol(out_text, golden_path, nt, nheader, nr=None):
     got = out_text.split("\n")
     ref = open(golden_path).read().split("\n")
