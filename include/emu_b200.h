@@ -58,6 +58,7 @@ void emub_model_destroy(emub_model *m);
 int emub_model_nthetas(const emub_model *m);         /* modelstruct.c:301-308 */
 int emub_model_nregression_fns(const emub_model *m); /* modelstruct.c:319 */
 int emub_model_slots(const emub_model *m);
+int emub_model_kernel(const emub_model *m);          /* EMUB_POWEREXP / EMUB_MATERN32 / EMUB_MATERN52 */
 /* replace the training vector (same design): the PCA components of one multivariate model share X
  * (multi_modelstruct.c:121-148) */
 int emub_model_set_training(emub_model *m, const double *y);
@@ -82,6 +83,12 @@ int emub_h_matrix(emub_model *m, double *H, int ldh);
 /* makeKVector_fnptr (emulator.c:578) for mq points at once: K (n x mq, row stride ldk),
  * K[i][q] = c(x_i, pts_q) with the 1e-10 clamp */
 int emub_k_vectors(emub_model *m, const double *thetas, const double *pts, int ldp, int mq, double *K, int ldk);
+
+/* chol_inverse_cov_matrix (emulate-fns.c:275-300) for a caller-owned symmetric positive definite n x n matrix
+ * (n = the model's nmodel_points; A row stride lda; only the model's factorisation workspace is used, not its design):
+ * Ainv (row stride ldi) <- A^-1, *logdet <- log det A = 2 sum log L_ii (the reference forms (prod L_ii)^2, :290-293).
+ * Returns EMUB_EDOM where the reference exits ("trying to cholesky a non postive def matrix", :282-285). */
+int emub_spd_inverse(emub_model *m, const double *A, int lda, double *Ainv, int ldi, double *logdet);
 
 /*
  * evalFnMulti / gradFnMulti / evalFnGradMulti (maxmultimin.c:288 / :416 / :615) for B points at

@@ -96,7 +96,9 @@ struct LaunchScope {
 
 // one kernel launch of the factorisation sequence (depth-first order of the recursion)
 enum { STEP_POTF2 = 0, STEP_TRSM, STEP_SYRK, STEP_TMUL, STEP_WMUL };
-struct FactorStep { int type; int off, cnt; int kblk; double flops; };
+struct FactorStep { int type; int off, cnt; int kblk; double flops; int full_only; };
+// a node [lo, hi) of the recursion on its right spine (root, right child of the root, ...), split at mid
+struct SpineNode { int lo, mid, hi; };
 
 struct emub_model {
 	emub_ctx *ctx;
@@ -109,6 +111,7 @@ struct emub_model {
 	struct QueryWs *qws;    // query workspace shared by every emulator of this model (lazily allocated)
 	GemmTask *dTasks;
 	std::vector<FactorStep> steps;
+	std::vector<SpineNode> spine;
 	int lauum_off, lauum_cnt;
 	double lauum_flops;
 	double *bufA, *bufW, *bufT;
@@ -246,44 +249,52 @@ extern "C" long long emub_launch_count(emub_ctx *c) { return c ? c->launches : 0
 //   T = L21 W11 ;  W21 = -W22 T                     triangular-inverse merge; T lives in the dead A21 region
 // Every GEMM therefore runs with K = the size of the half it multiplies against (94% of the flops at
 // K >= 1024 for n = 4096), instead of the K = 128 rank updates of a panel-by-panel sweep.
-static void build_factor(emub_model *m, int lo, int hi, std::vector<GemmTask> &tasks)
+//
+// The Cholesky factor itself only needs the inverses of LEFT halves (they feed the TRSM of their parent): the merge of
+// a node on the right spine of the recursion (the root, its right child, ...) produces blocks of W that nothing but the
+// full inverse uses.  Those steps are marked full_only: a value-only likelihood (evalFnMulti, maxmultimin.c:288-394)
+// skips them and costs n^3/3 + n^3/21 flops instead of 2n^3/3 (+ n^3/3 for W^T W); L and the W blocks it does build are
+// the same bits either way.
+static void build_factor(emub_model *m, int lo, int hi, std::vector<GemmTask> &tasks, bool on_spine)
 {
 	const long long ld = m->npad;
 	auto off = [&](int bi, int bj) { return (long long)bi * TB * ld + (long long)bj * TB; };
 	auto by_k = [](const GemmTask &a, const GemmTask &b) { return a.klen > b.klen; };
-	auto emit = [&](int type, std::vector<GemmTask> &t) {
+	auto emit = [&](int type, std::vector<GemmTask> &t, int full_only) {
 		std::stable_sort(t.begin(), t.end(), by_k);
-		FactorStep st{type, (int)tasks.size(), (int)t.size(), 0, 0.0};
+		FactorStep st{type, (int)tasks.size(), (int)t.size(), 0, 0.0, full_only};
 		for (auto &x : t) { tasks.push_back(x); st.flops += task_flops(x); }
 		m->steps.push_back(st);
 	};
 	if (hi - lo == 1) {
-		m->steps.push_back({STEP_POTF2, 0, 0, lo, 2.0 * TB * TB * TB / 3.0});
+		m->steps.push_back({STEP_POTF2, 0, 0, lo, 2.0 * TB * TB * TB / 3.0, 0});
+		if (on_spine) m->spine.push_back({lo, hi, hi});
 		return;
 	}
 	const int mid = lo + (hi - lo + 1) / 2;
-	build_factor(m, lo, mid, tasks);
+	if (on_spine) m->spine.push_back({lo, mid, hi});
+	build_factor(m, lo, mid, tasks, false);
 	std::vector<GemmTask> t;
 	// L(i,j) = sum_{k in [lo, j]} A(i,k) W(j,k)^T          A = bufA KMAJOR, B = bufW KMAJOR -> bufT
 	for (int i = mid; i < hi; i++)
 		for (int j = lo; j < mid; j++) t.push_back({off(i, lo), off(j, lo), off(i, j), (j - lo + 1) * TB, TASK_TRIM_END_SC0});
-	emit(STEP_TRSM, t);
+	emit(STEP_TRSM, t, 0);
 	t.clear();
 	// A(i,j) -= sum_{k in [lo, mid)} L(i,k) L(j,k)^T      A, B = bufT KMAJOR -> bufA
 	for (int i = mid; i < hi; i++)
 		for (int j = mid; j <= i; j++) t.push_back({off(i, lo), off(j, lo), off(i, j), (mid - lo) * TB, (i == j) ? TASK_LOWER : 0});
-	emit(STEP_SYRK, t);
-	build_factor(m, mid, hi, tasks);
+	emit(STEP_SYRK, t, 0);
+	build_factor(m, mid, hi, tasks, on_spine);
 	t.clear();
 	// T(i,j) = sum_{k in [j, mid)} L(i,k) W(k,j)           A = bufT KMAJOR, B = bufW RMAJOR -> bufA
 	for (int i = mid; i < hi; i++)
 		for (int j = lo; j < mid; j++) t.push_back({off(i, j), off(j, j), off(i, j), (mid - j) * TB, TASK_TRIM_BEGIN_SC1});
-	emit(STEP_TMUL, t);
+	emit(STEP_TMUL, t, on_spine ? 1 : 0);
 	t.clear();
 	// W(i,j) = - sum_{k in [mid, i]} W(i,k) T(k,j)         A = bufW KMAJOR, B = bufA RMAJOR -> bufW
 	for (int i = mid; i < hi; i++)
 		for (int j = lo; j < mid; j++) t.push_back({off(i, mid), off(mid, j), off(i, j), (i + 1 - mid) * TB, TASK_TRIM_END_SR0});
-	emit(STEP_WMUL, t);
+	emit(STEP_WMUL, t, on_spine ? 1 : 0);
 }
 
 static void build_schedules(emub_model *m, std::vector<GemmTask> &tasks)
@@ -291,7 +302,7 @@ static void build_schedules(emub_model *m, std::vector<GemmTask> &tasks)
 	const long long ld = m->npad;
 	const int nb = m->nblk;
 	auto off = [&](int bi, int bj) { return (long long)bi * TB * ld + (long long)bj * TB; };
-	build_factor(m, 0, nb, tasks);
+	build_factor(m, 0, nb, tasks, true);
 	// Cinv(i,j) = sum_{k >= i} W(k,i)^T W(k,j), i >= j     A = W RMAJOR, B = W RMAJOR
 	m->lauum_off = (int)tasks.size();
 	m->lauum_flops = 0;
@@ -408,6 +419,7 @@ extern "C" void emub_model_destroy(emub_model *m)
 extern "C" int emub_model_nthetas(const emub_model *m) { return m ? m->nth : 0; }
 extern "C" int emub_model_nregression_fns(const emub_model *m) { return m ? m->p : 0; }
 extern "C" int emub_model_slots(const emub_model *m) { return m ? m->nslots : 0; }
+extern "C" int emub_model_kernel(const emub_model *m) { return m ? m->kernel : 0; }
 
 static void few_graphs_clear(QueryWs *w)
 {
@@ -527,13 +539,15 @@ static void launch_kcross(emub_model *m, cudaStream_t st, const double *consts, 
 }
 
 // L (bufT) and W = L^-1 (bufW) from C (bufA) for `count` slots starting at s0
-static void run_factor(emub_model *m, cudaStream_t st, int s0, int count)
+// full = false: the factor only (the merges of the right spine of the recursion are skipped, see build_factor)
+static void run_factor(emub_model *m, cudaStream_t st, int s0, int count, bool full)
 {
 	emub_ctx *c = m->ctx;
 	const int ld = m->npad;
 	const long long ms = (long long)m->mat;
 	double *A = m->bufA + (size_t)s0 * m->mat, *W = m->bufW + (size_t)s0 * m->mat, *T = m->bufT + (size_t)s0 * m->mat;
 	for (const FactorStep &s : m->steps) {
+		if (s.full_only && !full) continue;
 		const GemmTask *tk = m->dTasks + s.off;
 		switch (s.type) {
 		case STEP_POTF2: {
@@ -572,11 +586,29 @@ static void run_regression(emub_model *m, cudaStream_t st, int s0, int count, in
 	emub_ctx *c = m->ctx;
 	const long long sUG = (long long)m->npad * m->ncp;
 	const int nchunk_cols = (m->p + 1 + 7) / 8;
-	double *W = m->bufW + (size_t)s0 * m->mat;
-	double *UG = m->dUG + (size_t)s0 * sUG;
-	{
-		LaunchScope ls(c, EMUB_K_SKINNY, count * 4.0 * (double)m->mat * nchunk_cols, st);
-		k_tri_rows_times<<<dim3(m->npad / 32, nchunk_cols, count), 256, 0, st>>>(W, (long long)m->mat, m->npad, m->dYh, sUG, m->dComp + s0, m->ncp, UG, sUG);
+	double *W = m->bufW + (size_t)s0 * m->mat, *L = m->bufT + (size_t)s0 * m->mat;
+	double *UG = m->dUG + (size_t)s0 * sUG, *AB = m->dAB + (size_t)s0 * sUG;
+	// UG = L^-1 [y | H] by block forward substitution down the right spine of the recursion: for a spine node
+	// [lo, hi) split at mid,  u[lo:mid] = W11 b[lo:mid]  (W11 = inverse of the left half, built by every factorisation),
+	// b[mid:hi] -= L21 u[lo:mid].  b starts as Yh and lives in AB (free until the gradient stage).  The same launches
+	// serve the value-only and the gradient path, so both return the same bits.
+	const int *comp = m->dComp + s0;
+	for (size_t lv = 0; lv < m->spine.size(); lv++) {
+		const SpineNode nd = m->spine[lv];
+		const int r_lo = nd.lo * TB, r_mid = nd.mid * TB, r_hi = nd.hi * TB;
+		const double *bsrc = lv == 0 ? m->dYh : AB;
+		const long long bstride = sUG;
+		const int *bcomp = lv == 0 ? comp : nullptr;
+		{
+			LaunchScope ls(c, EMUB_K_SKINNY, count * 4.0 * (double)(r_mid - r_lo) * (r_mid - r_lo) * nchunk_cols, st);
+			k_rows_times_range<true><<<dim3((r_mid - r_lo) / 32, nchunk_cols, count), 256, 0, st>>>(
+			    W, (long long)m->mat, m->npad, r_lo, r_lo, r_mid, bsrc, bstride, bcomp, nullptr, 0, nullptr, m->ncp, UG, sUG);
+		}
+		if (r_hi > r_mid) {
+			LaunchScope ls(c, EMUB_K_SKINNY, count * 8.0 * (double)(r_hi - r_mid) * (r_mid - r_lo) * nchunk_cols, st);
+			k_rows_times_range<false><<<dim3((r_hi - r_mid) / 32, nchunk_cols, count), 256, 0, st>>>(
+			    L, (long long)m->mat, m->npad, r_mid, r_lo, r_mid, UG, sUG, nullptr, bsrc, bstride, bcomp, m->ncp, AB, sUG);
+		}
 	}
 	{
 		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
@@ -651,11 +683,13 @@ static void run_group(emub_model *m, cudaStream_t st, int s0, int count, int nth
 	}
 	cudaMemsetAsync(m->dInfo + s0, 0, sizeof(int) * count, st);
 	launch_cov(m, st, count, m->dConsts + (size_t)s0 * CONST_STRIDE, m->bufA + (size_t)s0 * m->mat, (long long)m->mat, 1);
-	run_factor(m, st, s0, count);
+	// the whole triangular inverse is only needed for C^-1 (gradient) and for prediction (W K)
+	run_factor(m, st, s0, count, want_grad || emulator_mode);
 	run_regression(m, st, s0, count, emulator_mode);
 	if (want_grad) {
 		run_lauum(m, st, s0, count);
-		run_wt_times(m, st, s0, count, 1);
+		// alpha = W^T u; the exact-gradient mode also reads C^-1 H = W^T G (every column chunk)
+		run_wt_times(m, st, s0, count, m->exact_grad ? (m->p + 1 + 7) / 8 : 1);
 		run_gradient(m, st, s0, count);
 	}
 }
@@ -858,6 +892,41 @@ extern "C" int emub_k_vectors(emub_model *m, const double *thetas, const double 
 	return EMUB_OK;
 }
 
+// chol_inverse_cov_matrix (emulate-fns.c:275-300) for a caller-owned n x n matrix (n = the model's nmodel_points; the
+// design of the model is not used): Cholesky, log-determinant, explicit inverse on the engine's factorisation slot 0.
+extern "C" int emub_spd_inverse(emub_model *m, const double *A, int lda, double *Ainv, int ldi, double *logdet)
+{
+	if (!m || !A || !Ainv || lda < m->n || ldi < m->n) return set_err(EMUB_EINVAL, "emub_spd_inverse: bad argument%s");
+	emub_ctx *c = m->ctx;
+	CUDA_TRY(cudaSetDevice(c->device));
+	cudaStream_t st = c->streams[0];
+	const int n = m->n, npad = m->npad;
+	CUDA_TRY(cudaMemsetAsync(m->bufA, 0, m->mat * sizeof(double), st));
+	CUDA_TRY(cudaMemcpy2DAsync(m->bufA, sizeof(double) * npad, A, sizeof(double) * lda, sizeof(double) * n, n, cudaMemcpyHostToDevice, st));
+	if (npad > n) {
+		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
+		k_pad_identity<<<(npad - n + 127) / 128, 128, 0, st>>>(m->bufA, npad, n);
+	}
+	CUDA_TRY(cudaMemsetAsync(m->dInfo, 0, sizeof(int), st));
+	run_factor(m, st, 0, 1, true);
+	run_lauum(m, st, 0, 1);
+	CUDA_TRY(cudaMemcpy2DAsync(Ainv, sizeof(double) * ldi, m->bufA, sizeof(double) * npad, sizeof(double) * n, n, cudaMemcpyDeviceToHost, st));
+	std::vector<double> parts(m->nblk);
+	int info = 0;
+	CUDA_TRY(cudaMemcpyAsync(parts.data(), m->dLogdet, sizeof(double) * m->nblk, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaMemcpyAsync(&info, m->dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	CUDA_TRY(cudaGetLastError());
+	if (info) return set_err(EMUB_EDOM, "emub_spd_inverse: matrix not positive definite%s");
+	double sum = 0.0;
+	for (double v : parts) sum += v;
+	if (logdet) *logdet = 2.0 * sum;
+	// the engine keeps the lower tiles: mirror them (tiles above the diagonal were never written)
+	for (int i = 0; i < n; i++)
+		for (int j = i + 1; j < n; j++) Ainv[(size_t)i * ldi + j] = Ainv[(size_t)j * ldi + i];
+	return EMUB_OK;
+}
+
 extern "C" int emub_debug_fetch(emub_model *m, int b, int which, double *out, int ldo)
 {
 	if (!m || !out || b < 0 || b >= m->nslots || ldo < m->n) return set_err(EMUB_EINVAL, "emub_debug_fetch: bad argument%s");
@@ -900,7 +969,7 @@ extern "C" int emub_debug_cholesky(emub_model *m, const double *theta_less_amp, 
 	}
 	CUDA_TRY(cudaMemsetAsync(m->dInfo, 0, sizeof(int), st));
 	launch_cov(m, st, 1, m->dConsts, m->bufA, (long long)m->mat, 1);
-	run_factor(m, st, 0, 1);
+	run_factor(m, st, 0, 1, true);
 	CUDA_TRY(cudaStreamSynchronize(st));
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemcpy2D(L, sizeof(double) * ldl, m->bufT, sizeof(double) * m->npad, sizeof(double) * m->n, m->n, cudaMemcpyDeviceToHost));
@@ -918,9 +987,9 @@ extern "C" int emub_debug_cholesky(emub_model *m, const double *theta_less_amp, 
 
 // ---- prediction ------------------------------------------------------------------------------------------
 extern "C" void emub_emulator_destroy(emub_emulator *e);
-static int ensure_query_ws(emub_model *m)
+// every allocation of the workspace; on a failure the caller (ensure_query_ws) tears the half-built workspace down
+static int build_query_ws(emub_model *m)
 {
-	if (m->qws) return EMUB_OK;
 	QueryWs *w = new QueryWs();
 	memset(w, 0, sizeof(*w));
 	m->qws = w;
@@ -958,6 +1027,19 @@ static int ensure_query_ws(emub_model *m)
 	CUDA_TRY(cudaMalloc(&w->dTasks, tasks.size() * sizeof(GemmTask)));
 	CUDA_TRY(cudaMemcpy(w->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
 	return EMUB_OK;
+}
+
+// The workspace is installed only when every allocation succeeded: a failed cudaMalloc (dK alone is up to 1 GiB)
+// must not leave a workspace with null device pointers behind for the next predict call to launch kernels on.
+static int ensure_query_ws(emub_model *m)
+{
+	if (m->qws) return EMUB_OK;
+	const int rc = build_query_ws(m);
+	if (rc != EMUB_OK) {
+		free_query_ws(m);  // frees whatever was allocated and resets m->qws
+		cudaGetLastError();
+	}
+	return rc;
 }
 
 // back-projected outputs of a chunk are mqc x nt on the device and twice that in each pinned host buffer: grow them
@@ -1135,9 +1217,18 @@ static int few_set_prepare(emub_emulator *const *emus, int nr, cudaStream_t st, 
 			cudaFree(w->dFewSet); cudaFree(w->dFewConsts); cudaFree(w->dFew);
 			w->dFewSet = nullptr; w->dFewConsts = nullptr; w->dFew = nullptr;
 			w->few_cap = 0;
-			CUDA_TRY(cudaMalloc(&w->dFewSet, sizeof(FewSet) * (size_t)nr));
-			CUDA_TRY(cudaMalloc(&w->dFewConsts, sizeof(double) * (size_t)nr * CONST_STRIDE));
-			CUDA_TRY(cudaMalloc(&w->dFew, sizeof(double) * (size_t)nr * tstride));
+			if (cudaMalloc(&w->dFewSet, sizeof(FewSet) * (size_t)nr) != cudaSuccess ||
+			    cudaMalloc(&w->dFewConsts, sizeof(double) * (size_t)nr * CONST_STRIDE) != cudaSuccess ||
+			    cudaMalloc(&w->dFew, sizeof(double) * (size_t)nr * tstride) != cudaSuccess) {
+				// back to the state build_query_ws leaves: partial products for ONE emulator (emub_predict_few uses
+				// dFew without the tables); if even that does not fit, drop the workspace so that the next call rebuilds it
+				cudaGetLastError();
+				cudaFree(w->dFewSet); cudaFree(w->dFewConsts); cudaFree(w->dFew);
+				w->dFewSet = nullptr; w->dFewConsts = nullptr; w->dFew = nullptr;
+				if (cudaMalloc(&w->dFew, sizeof(double) * (size_t)tstride) == cudaSuccess) w->few_cap = 1;
+				else { cudaGetLastError(); free_query_ws(m); }
+				return set_err(EMUB_ENOMEM, "emub_predict_multi_few: out of device memory for the component tables%s");
+			}
 			w->few_cap = nr;
 		}
 		CUDA_TRY(cudaMemcpyAsync(w->dFewSet, hs.data(), sizeof(FewSet) * (size_t)nr, cudaMemcpyHostToDevice, st));

@@ -80,8 +80,8 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 	double *sXj = sm + d * CT;   // [d][64]
 	__shared__ double sc[CONST_STRIDE];
 	__shared__ double sh[MAXD];  // -0.5 / l_k^2 (scaling by 1/2 is exact: same bits as the literal (-1/2 dist) dist / l^2 up to D-5)
-	__shared__ double stab[64];
-	exp_table_load(stab);
+	__shared__ double stab[64 * EXP_REP];
+	exp_table_load<EXP_REP>(stab);
 	const int tid = threadIdx.x;
 	const double *cg = consts + b * const_stride;
 	for (int i = tid; i < 4 + 3 * d; i += 256) sc[i] = cg[i];
@@ -151,17 +151,17 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 			double v;
 			if (gi < n && gj < ncols) {
 				if (KERNEL == 1) {
-					v = exp_neg(e[r][c], stab) * sc[0];  // emulator.c:134
+					v = exp_neg<EXP_REP>(e[r][c], stab) * sc[0];  // emulator.c:134
 				} else {
 					// emulator.c:344-386 (Matern 3/2), :438-480 (Matern 5/2); e holds the squared distance
 					const double dist = sqrt(e[r][c]);
 					if (KERNEL == 2) {
 						const double root3 = 1.732050808;
-						v = (dist > 0.0) ? sc[0] * (1 + root3 * (dist / sc[2])) * exp_neg(-root3 * (dist / sc[2]), stab) : sc[0];
+						v = (dist > 0.0) ? sc[0] * (1 + root3 * (dist / sc[2])) * exp_neg<EXP_REP>(-root3 * (dist / sc[2]), stab) : sc[0];
 					} else {
 						const double root5 = 2.236067978;
 						const double dr = dist / sc[2];
-						v = (dist > 0.0) ? sc[0] * (1 + root5 * dr + (5.0 / 3.0) * dr * dr) * exp_neg(-root5 * dr, stab) : sc[0];
+						v = (dist > 0.0) ? sc[0] * (1 + root5 * dr + (5.0 / 3.0) * dr * dr) * exp_neg<EXP_REP>(-root5 * dr, stab) : sc[0];
 					}
 				}
 				if (same & (1u << (r * 4 + c))) v += sc[1];
@@ -192,32 +192,44 @@ __global__ void k_build_yh(const double *__restrict__ X, const double *__restric
 	if (order >= 3) for (int k = 0; k < d; k++) row[2 + 2 * d + k] = x[k] * x[k] * x[k];
 }
 
+// identity on the padding of a caller-supplied matrix (rows / columns [n, npad); the rest of the padding is already 0)
+__global__ void k_pad_identity(double *__restrict__ A, int npad, int n)
+{
+	const int i = n + blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < npad) A[(size_t)i * npad + i] = 1.0;
+}
+
 // ---- skinny products ---------------------------------------------------------------------------------
-// (a) OUT[i][c0..c0+8) = sum_{j <= i} W[i][j] * V[j][c0..c0+8)   (W lower triangular, npad x npad)
-// grid (npad/32, ncp/8, B), 256 threads: one warp per 4 rows.
-// V of slot b is Vbase + comp[b] * strideV (the training vector / PCA component the slot evaluates)
-__global__ void __launch_bounds__(256) k_tri_rows_times(const double *__restrict__ Wbase, long long strideW, int ld,
-                                                        const double *__restrict__ Vbase, long long strideV,
-                                                        const int *__restrict__ comp, int ncp,
-                                                        double *__restrict__ Obase, long long strideO)
+// (a) rows [r_lo, r_lo + 32 gridDim.x) of   OUT = [S -] M[:, j_lo:j_hi) V[j_lo:j_hi)   on 8 columns c0..c0+8 of V:
+//     TRI:  acc(i) = sum_{j in [j_lo, min(i, j_hi - 1)]} M[i][j] V[j]     (M = W lower triangular; OUT = acc)
+//     else: acc(i) = sum_{j in [j_lo, j_hi)} M[i][j] V[j]                  (M = L21; OUT = S - acc when S is given)
+// These are the two steps of the block forward substitution L u = [y | H] (emub_api.cu: run_regression).
+// grid (nrows/32, ncp/8, B), 256 threads: one warp per 4 rows, lanes stride over the columns j.
+// V (and S) of slot b: base + comp[b] * stride when comp is given (the training vector / PCA component the slot
+// evaluates, shared by all slots), else base + b * stride (per-slot buffer).
+template <bool TRI>
+__global__ void __launch_bounds__(256) k_rows_times_range(const double *__restrict__ Mbase, long long strideM, int ld, int r_lo,
+                                                          int j_lo, int j_hi, const double *__restrict__ Vbase, long long strideV,
+                                                          const int *__restrict__ compV, const double *Sbase, long long strideS,
+                                                          const int *__restrict__ compS, int ncp, double *Obase, long long strideO)
 {
 	const int b = blockIdx.z, c0 = blockIdx.y * 8;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int r0 = blockIdx.x * 32 + warp * 4;
-	const double *W = Wbase + b * strideW;
-	const double *V = Vbase + (comp ? comp[b] : 0) * strideV;
+	const int r0 = r_lo + blockIdx.x * 32 + warp * 4;
+	const double *M = Mbase + b * strideM;
+	const double *V = Vbase + (compV ? compV[b] : b) * strideV;
 	double acc[4][8];
 #pragma unroll
 	for (int r = 0; r < 4; r++)
 #pragma unroll
 		for (int c = 0; c < 8; c++) acc[r][c] = 0.0;
-	const int jmax = r0 + 3;
-	for (int j = lane; j <= jmax; j += 32) {
+	const int jmax = TRI ? min(r0 + 3, j_hi - 1) : j_hi - 1;
+	for (int j = j_lo + lane; j <= jmax; j += 32) {
 		const double4 v0 = *reinterpret_cast<const double4 *>(V + (size_t)j * ncp + c0);
 		const double4 v1 = *reinterpret_cast<const double4 *>(V + (size_t)j * ncp + c0 + 4);
 #pragma unroll
 		for (int r = 0; r < 4; r++) {
-			const double w = (j <= r0 + r) ? W[(size_t)(r0 + r) * ld + j] : 0.0;
+			const double w = (!TRI || j <= r0 + r) ? M[(size_t)(r0 + r) * ld + j] : 0.0;
 			acc[r][0] += w * v0.x; acc[r][1] += w * v0.y; acc[r][2] += w * v0.z; acc[r][3] += w * v0.w;
 			acc[r][4] += w * v1.x; acc[r][5] += w * v1.y; acc[r][6] += w * v1.z; acc[r][7] += w * v1.w;
 		}
@@ -233,11 +245,12 @@ __global__ void __launch_bounds__(256) k_tri_rows_times(const double *__restrict
 		}
 	if (lane < 4) {
 		double *O = Obase + b * strideO + (size_t)(r0 + lane) * ncp + c0;
+		const double *S = Sbase ? Sbase + (compS ? compS[b] : b) * strideS + (size_t)(r0 + lane) * ncp + c0 : nullptr;
 #pragma unroll
 		for (int r = 0; r < 4; r++)
 			if (lane == r)
 #pragma unroll
-				for (int c = 0; c < 8; c++) O[c] = acc[r][c];
+				for (int c = 0; c < 8; c++) O[c] = S ? S[c] - acc[r][c] : acc[r][c];
 	}
 }
 
@@ -457,8 +470,8 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 	double *sAi = sm + 2 * d * CT, *sAj = sAi + CT;
 	__shared__ double sc[CONST_STRIDE];
 	__shared__ double red[8][MAXD];
-	__shared__ double stab[64];
-	exp_table_load(stab);
+	__shared__ double stab[64 * EXP_REP];
+	exp_table_load<EXP_REP>(stab);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const double *cg = consts + (size_t)b * CONST_STRIDE;
 	for (int i = tid; i < 4 + 3 * d; i += 256) sc[i] = cg[i];
@@ -516,7 +529,7 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 #pragma unroll
 		for (int r = 0; r < 4; r++)
 #pragma unroll
-			for (int c = 0; c < 4; c++) w[r][c] *= exp_neg(-ex[r][c], stab);
+			for (int c = 0; c < 4; c++) w[r][c] *= exp_neg<EXP_REP>(-ex[r][c], stab);
 		for (int k = 0; k < d; k++) {
 			double s = 0.0;
 #pragma unroll
@@ -543,7 +556,7 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 				for (int c = 0; c < 4; c++) {
 					const double dl = xi - sXj[k * CT + tx + 16 * c];
 					const double q = dl * dl;
-					s += w[r][c] * (q * exp_neg(-ak * q, stab));
+					s += w[r][c] * (q * exp_neg<EXP_REP>(-ak * q, stab));
 				}
 			}
 #pragma unroll
@@ -564,7 +577,7 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 					r2 += dl * dl;
 				}
 				const double t = root * (sqrt(r2) / rho);
-				const double f = (KERNEL == 2) ? t * t * exp_neg(-t, stab) : (t * t / 3.0) * (1.0 + t) * exp_neg(-t, stab);
+				const double f = (KERNEL == 2) ? t * t * exp_neg<EXP_REP>(-t, stab) : (t * t / 3.0) * (1.0 + t) * exp_neg<EXP_REP>(-t, stab);
 				s += w[r][c] * f;
 			}
 #pragma unroll

@@ -29,7 +29,7 @@ FAMILIES = ["cov", "potf2", "gemm_chol", "gemm_trtri", "gemm_lauum", "skinny", "
 SYMBOLS = [
     "emub_ctx_create", "emub_ctx_destroy", "emub_last_error", "emub_version", "emub_ctx_stream",
     "emub_ctx_set_groups", "emub_ctx_use_graphs", "emub_model_create", "emub_model_destroy", "emub_model_nthetas",
-    "emub_model_nregression_fns", "emub_model_slots", "emub_model_set_training", "emub_model_set_training_multi",
+    "emub_model_nregression_fns", "emub_model_slots", "emub_model_kernel", "emub_spd_inverse", "emub_model_set_training", "emub_model_set_training_multi",
     "emub_model_ncomponents", "emub_model_set_gradient_mode", "emub_model_gradient_mode", "emub_loglik_grad_batch_comp", "emub_emulator_create_comp", "emub_predict_multi", "emub_predict_multi_few", "emub_cov_matrix",
     "emub_h_matrix", "emub_k_vectors", "emub_loglik_grad_batch", "emub_loglik_grad_batch_dev",
     "emub_ctx_synchronize", "emub_loglik_extras", "emub_emulator_create", "emub_emulator_destroy",
@@ -77,6 +77,8 @@ def lib():
     L.emub_model_nthetas.argtypes = [_vp]
     L.emub_model_nregression_fns.argtypes = [_vp]
     L.emub_model_slots.argtypes = [_vp]
+    L.emub_model_kernel.argtypes = [_vp]
+    L.emub_spd_inverse.argtypes = [_vp, _dp, _ci, _dp, _ci, _dp]
     L.emub_model_set_training.argtypes = [_vp, _dp]
     L.emub_model_set_training_multi.argtypes = [_vp, _dp, _ci, _ci]
     L.emub_model_ncomponents.argtypes = [_vp]
@@ -254,6 +256,14 @@ class Model:
     def loglik_grad_batch_dev(self, d_thetas_ptr, B, want_grad, d_out_ptr):
         _check(self.L.emub_loglik_grad_batch_dev(self.h, d_thetas_ptr, B, 1 if want_grad else 0, d_out_ptr))
 
+    def spd_inverse(self, A):
+        """chol_inverse_cov_matrix (emulate-fns.c:275) for a caller-owned n x n matrix: (A^-1, log det A)."""
+        A = _c(A)
+        out = np.empty_like(A)
+        ld = ctypes.c_double()
+        _check(self.L.emub_spd_inverse(self.h, _P(A), self.n, _P(out), self.n, ctypes.byref(ld)))
+        return out, ld.value
+
     def debug_fetch(self, slot, which):
         out = np.empty((self.n, self.n))
         _check(self.L.emub_debug_fetch(self.h, slot, which, _P(out), self.n))
@@ -359,11 +369,21 @@ HOST_SYMBOLS = ["emub_estimate_default_opts", "emub_sample_scales", "emub_optimi
 class EstimateOpts(ctypes.Structure):
     _fields_ = [("max_tries", _ci), ("nchains", _ci), ("seed", ctypes.c_ulonglong), ("step_size", ctypes.c_double),
                 ("tol", ctypes.c_double), ("eps_abs", ctypes.c_double), ("step_max", _ci), ("first_component", _ci),
-                ("component_stride", _ci), ("polish_steps", _ci), ("polish_eps", ctypes.c_double)]
+                ("component_stride", _ci), ("polish_steps", _ci), ("polish_eps", ctypes.c_double), ("value_policy", _ci)]
+
+
+VALUE_ADAPTIVE, VALUE_ALWAYS_GRADIENT, VALUE_ONLY = 0, 1, 2
 
 
 class EstimateStats(ctypes.Structure):
-    _fields_ = [("evaluations", _ll), ("batches", _ll), ("success_count", _ci), ("finite_count", _ci)]
+    _fields_ = [("evaluations", _ll), ("batches", _ll), ("success_count", _ci), ("finite_count", _ci),
+                ("value_evaluations", _ll), ("repeated_points", _ll), ("unused_gradients", _ll)]
+
+
+def _stats_dict(rc, st):
+    return dict(rc=rc, evaluations=st.evaluations, batches=st.batches, success_count=st.success_count,
+                finite_count=st.finite_count, value_evaluations=st.value_evaluations, repeated_points=st.repeated_points,
+                unused_gradients=st.unused_gradients)
 
 
 _hostlib = None
@@ -411,7 +431,8 @@ def random_init(seed, try_index, ranges):
     return x
 
 
-def estimate_thetas(model, ranges=None, max_tries=50, nchains=0, seed=1, starts=None, polish_steps=0):
+def estimate_thetas(model, ranges=None, max_tries=50, nchains=0, seed=1, starts=None, polish_steps=0, value_policy=VALUE_ADAPTIVE,
+                    step_max=None):
     """maxWithMultiMin (maxmultimin.c:47) over the batched GPU evaluator.  Returns (thetas[nthetas], best log
     likelihood, stats dict).  starts: optional (max_tries x nthetas) explicit start points.  polish_steps > 0 adds the
     optional refinement run from the best point (emub_estimate.h)."""
@@ -424,7 +445,9 @@ def estimate_thetas(model, ranges=None, max_tries=50, nchains=0, seed=1, starts=
     if starts is not None:
         starts = _c(starts).reshape(-1, model.nthetas)
         max_tries = starts.shape[0]
-    o.max_tries, o.nchains, o.seed, o.polish_steps = max_tries, nchains, seed, polish_steps
+    o.max_tries, o.nchains, o.seed, o.polish_steps, o.value_policy = max_tries, nchains, seed, polish_steps, value_policy
+    if step_max is not None:
+        o.step_max = step_max
     th = np.zeros(model.nthetas)
     best = ctypes.c_double()
     st = EstimateStats()
@@ -432,11 +455,11 @@ def estimate_thetas(model, ranges=None, max_tries=50, nchains=0, seed=1, starts=
                                      _P(th), ctypes.byref(best), ctypes.byref(st))
     if rc not in (OK, EDOM):
         _check(rc)
-    return th, best.value, dict(rc=rc, evaluations=st.evaluations, batches=st.batches, success_count=st.success_count,
-                                finite_count=st.finite_count)
+    return th, best.value, _stats_dict(rc, st)
 
 
-def estimate_thetas_multi(model, ncomp, ranges=None, max_tries=50, nchains=0, seed=1):
+def estimate_thetas_multi(model, ncomp, ranges=None, max_tries=50, nchains=0, seed=1, value_policy=VALUE_ADAPTIVE, step_max=None,
+                          first_component=0, component_stride=1):
     """estimate_multi (multivar_support.c:20) with the restart fronts of all ncomp components merged into one batch.
     Returns (thetas[ncomp, nthetas], best log likelihoods[ncomp], stats)."""
     H = host_lib()
@@ -445,15 +468,17 @@ def estimate_thetas_multi(model, ncomp, ranges=None, max_tries=50, nchains=0, se
     ranges = _c(ranges)
     o = EstimateOpts()
     H.emub_estimate_default_opts(ctypes.byref(o))
-    o.max_tries, o.nchains, o.seed = max_tries, nchains, seed
+    o.max_tries, o.nchains, o.seed, o.value_policy = max_tries, nchains, seed, value_policy
+    o.first_component, o.component_stride = first_component, component_stride
+    if step_max is not None:
+        o.step_max = step_max
     th = np.zeros((ncomp, model.nthetas))
     best = np.zeros(ncomp)
     st = EstimateStats()
     rc = H.emub_estimate_thetas_multi(model.h, ncomp, _P(ranges), ctypes.byref(o), _P(th), _P(best), ctypes.byref(st))
     if rc not in (OK, EDOM):
         _check(rc)
-    return th, best, dict(rc=rc, evaluations=st.evaluations, batches=st.batches, success_count=st.success_count,
-                          finite_count=st.finite_count)
+    return th, best, _stats_dict(rc, st)
 
 
 def estimate_thetas_multi_devices(devices, X, Z, kernel=POWEREXP, order=0, max_tries=50, nchains=0, seed=1, max_slots=0):
@@ -475,5 +500,4 @@ def estimate_thetas_multi_devices(devices, X, Z, kernel=POWEREXP, order=0, max_t
                                               max_slots, ctypes.byref(o), _P(th), _P(best), ctypes.byref(st))
     if rc not in (OK, EDOM):
         _check(rc)
-    return th, best, dict(rc=rc, evaluations=st.evaluations, batches=st.batches, success_count=st.success_count,
-                          finite_count=st.finite_count)
+    return th, best, _stats_dict(rc, st)

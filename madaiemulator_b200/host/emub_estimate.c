@@ -22,6 +22,7 @@ void emub_estimate_default_opts(emub_estimate_opts *o)
 	o->component_stride = 1;
 	o->polish_steps = 0;
 	o->polish_eps = 1e-3;
+	o->value_policy = EMUB_VALUE_ADAPTIVE;
 }
 
 /* modelstruct.c:188-213 */
@@ -90,13 +91,17 @@ typedef struct {
 	int first_try, try_stride;
 	unsigned long long seed;
 	int state;
+	int want_grad;        /* the pending request needs the gradient */
 	double *x, *g;        /* request point (nth1), returned gradient */
 	double f, sigma2;
 	int status;
-	/* last evaluated point, so that f(x) followed by df(x) costs one evaluation */
+	/* last evaluated point, so that f(x) followed by df(x) costs one evaluation when the gradient is already there */
 	double *cx, *cg;
 	double cf, csigma2;
-	int cstatus, cvalid;
+	int cstatus, cvalid, chas_grad, cgrad_used;
+	/* value-policy bookkeeping (per chain, so independent of thread timing) */
+	long long n_value_requests, n_followed;
+	long long value_evals, repeated, unused_grads;
 	/* result of this chain's restarts */
 	double best_lhood;
 	double *best_thetas;
@@ -118,12 +123,28 @@ typedef struct front {
 	int failed;
 } front_t;
 
-static void chain_request(chain_t *c, const double *x)
+/* value_request: the optimiser asked for f alone (it may or may not come back for the gradient at this point) */
+static void chain_request(chain_t *c, const double *x, int need_grad, int value_request)
 {
 	front_t *fr = c->fr;
-	if (c->cvalid && memcmp(c->cx, x, sizeof(double) * (size_t)fr->nth1) == 0) return;
+	const int same = c->cvalid && memcmp(c->cx, x, sizeof(double) * (size_t)fr->nth1) == 0;
+	if (same && need_grad && !value_request && c->chas_grad) c->cgrad_used = 1;
+	if (same && (c->chas_grad || !need_grad)) return;
+	int want_grad = need_grad;
+	if (value_request) {
+		const int policy = fr->opts->value_policy;
+		c->n_value_requests++;
+		if (policy == EMUB_VALUE_ALWAYS_GRADIENT) want_grad = 1;
+		else if (policy == EMUB_VALUE_ONLY) want_grad = 0;
+		else want_grad = c->n_value_requests <= 4 || 100 * c->n_followed >= 62 * (c->n_value_requests - 1);
+	} else if (same) {
+		/* value-only point the optimiser now wants the gradient of: evaluated twice */
+		c->repeated++;
+	}
+	if (c->cvalid && c->chas_grad && !c->cgrad_used) c->unused_grads++; /* the cached gradient is about to be dropped unread */
 	pthread_mutex_lock(&fr->mu);
 	memcpy(c->x, x, sizeof(double) * (size_t)fr->nth1);
+	c->want_grad = want_grad;
 	c->state = REQ_PENDING;
 	fr->npending++;
 	if (fr->npending >= fr->nactive) pthread_cond_signal(&fr->cv_disp);
@@ -136,25 +157,35 @@ static void chain_request(chain_t *c, const double *x)
 	c->csigma2 = c->sigma2;
 	c->cstatus = c->status;
 	c->cvalid = 1;
+	c->chas_grad = want_grad;
+	c->cgrad_used = need_grad && !value_request;
+	if (!want_grad) c->value_evals++;
 }
 
 /* evalFnMulti / gradFnMulti / evalFnGradMulti as the optimiser sees them (maxmultimin.c:288, :416, :615) */
 static double cb_f(const double *x, void *ctx)
 {
 	chain_t *c = (chain_t *)ctx;
-	chain_request(c, x);
+	chain_request(c, x, 0, 1);
 	return c->cf;
+}
+static void note_followed(chain_t *c, const double *x)
+{
+	/* a gradient request at the point of the last value request: the line search accepted that trial point */
+	if (c->cvalid && !c->cgrad_used && memcmp(c->cx, x, sizeof(double) * (size_t)c->fr->nth1) == 0) c->n_followed++;
 }
 static void cb_df(const double *x, void *ctx, double *g)
 {
 	chain_t *c = (chain_t *)ctx;
-	chain_request(c, x);
+	note_followed(c, x);
+	chain_request(c, x, 1, 0);
 	memcpy(g, c->cg, sizeof(double) * (size_t)c->fr->nth1);
 }
 static void cb_fdf(const double *x, void *ctx, double *f, double *g)
 {
 	chain_t *c = (chain_t *)ctx;
-	chain_request(c, x);
+	note_followed(c, x);
+	chain_request(c, x, 1, 0);
 	*f = c->cf;
 	memcpy(g, c->cg, sizeof(double) * (size_t)c->fr->nth1);
 }
@@ -183,7 +214,7 @@ static void run_restart(chain_t *c, int try_index, emub_bfgs *bf)
 	if (status == EMUB_BFGS_OK) c->success_count++;
 	memcpy(x_final, emub_bfgs_x(bf), sizeof(double) * (size_t)nth1);
 	/* sigma re-estimate and score at the final point: one evaluation gives both (:757, :103) */
-	chain_request(c, x_final);
+	chain_request(c, x_final, 0, 0);
 	const double likelihood = -1.0 * c->cf;
 	if (c->cstatus == 0 && isfinite(likelihood) && isfinite(c->csigma2) && c->csigma2 > 0.0) {
 		c->finite_count++;
@@ -270,11 +301,27 @@ static int estimate_impl(emub_model *model, int ncomp, const double *ranges, con
 					best[k] = best2[k];
 					memcpy(thetas_out + (size_t)k * nth, th2 + (size_t)k * nth, sizeof(double) * (size_t)nth);
 				}
-			if (stats) { stats->evaluations += st2.evaluations; stats->batches += st2.batches; }
+			if (stats) {
+				stats->evaluations += st2.evaluations; stats->batches += st2.batches;
+				stats->value_evaluations += st2.value_evaluations; stats->repeated_points += st2.repeated_points;
+				stats->unused_gradients += st2.unused_gradients;
+			}
 		} else
 			rc = rc2;
 		free(th2); free(best2);
 	}
+	/* Matern kernels: hand the result over in the convention the covariance FUNCTIONS read (emulator.c:355-356,
+	 * :448-449: amplitude and nugget raw, log rho), which is what emub_emulator_create / alloc_emulator_struct, a
+	 * MODEL_SNAPSHOT_FILE and interactive_mode consume.  The chains work on (log sigma^2 | log nugget, log rho)
+	 * (deviation D-2: unit amplitude and e^theta_1 nugget during training, like the power-exponential kernel), so
+	 * amp = sigma^2 and nugget = e^theta_1 -- the same C = sigma^2 c + e^theta_1 delta the power-exponential
+	 * emulator builds from (log sigma^2, theta_1, ..) (emulator_struct.c:28, emulator.c:116-117). */
+	if (emub_model_kernel(model) != EMUB_POWEREXP)
+		for (int k = 0; k < ncomp; k++)
+			if (best[k] != SCREWUPVALUE) {
+				thetas_out[(size_t)k * nth] = exp(thetas_out[(size_t)k * nth]);
+				thetas_out[(size_t)k * nth + 1] = exp(thetas_out[(size_t)k * nth + 1]);
+			}
 	if (best_lhood) memcpy(best_lhood, best, sizeof(double) * (size_t)ncomp);
 	free(best);
 	return rc;
@@ -312,7 +359,26 @@ static int estimate_front(emub_model *model, int ncomp, const double *ranges, co
 		c->best_thetas = (double *)calloc(1, vb);
 	}
 	pthread_t *tids = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nchains);
-	for (int i = 0; i < nchains; i++) pthread_create(&tids[i], NULL, chain_main, &fr.chains[i]);
+	int nstarted = 0, thread_failed = 0;
+	{
+		/* a chain parks in the evaluation front until every live chain has asked, so all of them need a thread of their
+		 * own; if one cannot be created the front is shrunk to the chains that run (their restarts are then incomplete
+		 * and the call reports the failure) */
+		pthread_attr_t at;
+		pthread_attr_init(&at);
+		pthread_attr_setstacksize(&at, 1 << 20);
+		for (int i = 0; i < nchains; i++) {
+			if (pthread_create(&tids[i], &at, chain_main, &fr.chains[i]) != 0) { thread_failed = 1; break; }
+			nstarted++;
+		}
+		pthread_attr_destroy(&at);
+		if (thread_failed) {
+			pthread_mutex_lock(&fr.mu);
+			fr.nactive -= nchains - nstarted;
+			pthread_cond_signal(&fr.cv_disp);
+			pthread_mutex_unlock(&fr.mu);
+		}
+	}
 
 	/* dispatcher: whenever every live chain is waiting, evaluate the whole front in one GPU call */
 	double *bx = (double *)malloc(sizeof(double) * (size_t)nchains * fr.nth1);
@@ -327,19 +393,28 @@ static int estimate_front(emub_model *model, int ncomp, const double *ranges, co
 	for (;;) {
 		while (fr.nactive > 0 && fr.npending < fr.nactive) pthread_cond_wait(&fr.cv_disp, &fr.mu);
 		if (fr.nactive == 0) break;
-		int B = 0;
-		for (int i = 0; i < nchains; i++)
-			if (fr.chains[i].state == REQ_PENDING) {
-				memcpy(bx + (size_t)B * fr.nth1, fr.chains[i].x, sizeof(double) * (size_t)fr.nth1);
-				bcomp[B] = fr.chains[i].comp;
-				who[B++] = i;
-			}
+		/* the front in two batched calls: the points that need the gradient, then the value-only ones */
+		int B = 0, Bg = 0;
+		for (int pass = 1; pass >= 0; pass--) {
+			for (int i = 0; i < nchains; i++)
+				if (fr.chains[i].state == REQ_PENDING && fr.chains[i].want_grad == pass) {
+					memcpy(bx + (size_t)B * fr.nth1, fr.chains[i].x, sizeof(double) * (size_t)fr.nth1);
+					bcomp[B] = fr.chains[i].comp;
+					who[B++] = i;
+				}
+			if (pass == 1) Bg = B;
+		}
 		pthread_mutex_unlock(&fr.mu);
-		int call = emub_loglik_grad_batch_comp(model, bx, bcomp, B, 1, bf, bg, bs, bst);
+		int call = EMUB_OK;
+		if (Bg > 0) { call = emub_loglik_grad_batch_comp(model, bx, bcomp, Bg, 1, bf, bg, bs, bst); fr.batches++; }
+		if (call == EMUB_OK && B > Bg) {
+			call = emub_loglik_grad_batch_comp(model, bx + (size_t)Bg * fr.nth1, bcomp + Bg, B - Bg, 0, bf + Bg, bg + (size_t)Bg * fr.nth1,
+			                                   bs + Bg, bst + Bg);
+			fr.batches++;
+		}
 		pthread_mutex_lock(&fr.mu);
 		if (call != EMUB_OK) { rc = call; fr.failed = 1; }
 		fr.evaluations += B;
-		fr.batches++;
 		for (int k = 0; k < B; k++) {
 			chain_t *c = &fr.chains[who[k]];
 			if (call == EMUB_OK) {
@@ -355,7 +430,8 @@ static int estimate_front(emub_model *model, int ncomp, const double *ranges, co
 		pthread_cond_broadcast(&fr.cv_done);
 	}
 	pthread_mutex_unlock(&fr.mu);
-	for (int i = 0; i < nchains; i++) pthread_join(tids[i], NULL);
+	for (int i = 0; i < nstarted; i++) pthread_join(tids[i], NULL);
+	if (thread_failed && rc == EMUB_OK) rc = EMUB_ENOMEM;
 
 	/* best per component over its chains, in chain order (deterministic) -- estimate_threaded.c:294-323 */
 	int succ = 0, fin = 0, nfailed_comp = 0;
@@ -376,7 +452,15 @@ static int estimate_front(emub_model *model, int ncomp, const double *ranges, co
 			for (int i = 0; i < fr.nth; i++) thetas_out[(size_t)k * fr.nth + i] = 0.0;
 		}
 	}
-	if (stats) { stats->evaluations = fr.evaluations; stats->batches = fr.batches; stats->success_count = succ; stats->finite_count = fin; }
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		stats->evaluations = fr.evaluations; stats->batches = fr.batches; stats->success_count = succ; stats->finite_count = fin;
+		for (int i = 0; i < nchains; i++) {
+			stats->value_evaluations += fr.chains[i].value_evals;
+			stats->repeated_points += fr.chains[i].repeated;
+			stats->unused_gradients += fr.chains[i].unused_grads;
+		}
+	}
 	for (int i = 0; i < nchains; i++) {
 		chain_t *c = &fr.chains[i];
 		free(c->x); free(c->g); free(c->cx); free(c->cg); free(c->best_thetas);
@@ -451,6 +535,7 @@ int emub_estimate_thetas_multi_devices_ranges(const int *devices, int ndev, cons
 	if (!devices || ndev < 1 || ndev > 64 || !X || !Z || ncomp < 1 || !thetas_out || !best_lhood) return EMUB_EINVAL;
 	dev_job jobs[64];
 	pthread_t th[64];
+	int started[64];
 	emub_estimate_opts o;
 	if (opts_in) o = *opts_in; else emub_estimate_default_opts(&o);
 	for (int g = 0; g < ndev; g++) {
@@ -459,16 +544,19 @@ int emub_estimate_thetas_multi_devices_ranges(const int *devices, int ndev, cons
 		j->device = devices[g]; j->g = g; j->ndev = ndev; j->X = X; j->Z = Z; j->ldx = ldx; j->n = n; j->d = d; j->ldz = ldz;
 		j->ncomp = ncomp; j->kernel = kernel; j->order = regression_order; j->max_slots = max_slots; j->opts = o;
 		j->thetas_out = thetas_out; j->best = best_lhood; j->ranges_in = ranges;
-		pthread_create(&th[g], NULL, dev_main, j);
+		started[g] = g > 0 && pthread_create(&th[g], NULL, dev_main, j) == 0;
 	}
 	int rc = EMUB_OK;
 	if (stats) memset(stats, 0, sizeof(*stats));
 	for (int g = 0; g < ndev; g++) {
-		pthread_join(th[g], NULL);
+		if (started[g]) pthread_join(th[g], NULL);
+		else dev_main(&jobs[g]); /* device 0, and any device whose thread could not be created, on the caller's thread */
 		if (jobs[g].rc != EMUB_OK && rc == EMUB_OK) rc = jobs[g].rc;
 		if (stats) {
 			stats->evaluations += jobs[g].stats.evaluations; stats->batches += jobs[g].stats.batches;
 			stats->success_count += jobs[g].stats.success_count; stats->finite_count += jobs[g].stats.finite_count;
+			stats->value_evaluations += jobs[g].stats.value_evaluations; stats->repeated_points += jobs[g].stats.repeated_points;
+			stats->unused_gradients += jobs[g].stats.unused_gradients;
 		}
 	}
 	return rc;

@@ -36,13 +36,24 @@ typedef struct {
 	 * ends is partly chance; the extra run costs a handful of batched evaluations and can only raise the likelihood. */
 	int polish_steps;
 	double polish_eps;
+	/* What a chain asks the GPU for when its optimiser wants the VALUE alone (evalFnMulti, maxmultimin.c:288 -- the
+	 * trial points of the line search).  The value-only evaluation costs 0.38 n^3 flops against n^3 with the gradient
+	 * (gradFnMulti, :416), but a trial point the line search accepts is asked for its gradient right away, and then
+	 * costs 1.38 n^3.  EMUB_VALUE_ADAPTIVE (default): per chain, value-only while fewer than 62% of its value requests
+	 * were followed by a gradient request at the same point, otherwise the gradient speculatively.  The optimiser sees
+	 * the same bits under every policy (the two evaluations return identical -L), so the result does not depend on it. */
+	int value_policy;
 } emub_estimate_opts;
+enum { EMUB_VALUE_ADAPTIVE = 0, EMUB_VALUE_ALWAYS_GRADIENT = 1, EMUB_VALUE_ONLY = 2 };
 
 typedef struct {
 	long long evaluations;    /* likelihood(+gradient) points evaluated on the GPU */
 	long long batches;        /* emub_loglik_grad_batch calls */
 	int success_count;        /* chains that stopped on |g| < eps_abs (maxmultimin.c:91-92) */
 	int finite_count;         /* restarts with a finite final likelihood (maxmultimin.c:110) */
+	long long value_evaluations;  /* of `evaluations`: value-only points (no triangular inverse, no C^-1, no gradient) */
+	long long repeated_points;    /* value-only points evaluated again with the gradient (the line search accepted them) */
+	long long unused_gradients;   /* gradients computed speculatively and never read by the optimiser */
 } emub_estimate_stats;
 
 void emub_estimate_default_opts(emub_estimate_opts *o);
@@ -60,6 +71,9 @@ void emub_random_init(unsigned long long seed, int try_index, const double *rang
  * log(sigma^2) re-estimated at the optimum (maxmultimin.c:757-769).  best_lhood: its log-likelihood
  * (maxmultimin.c:103).  Returns EMUB_OK, or EMUB_EDOM when no restart produced a finite likelihood
  * ("maximisation didn't work at all", maxmultimin.c:121-123).
+ * thetas_out is always in the convention emub_emulator_create / the covariance functions read:
+ * power-exponential (log sigma^2, log nugget, log lengths); Matern (sigma^2, nugget, log rho) -- amplitude and
+ * nugget RAW (emulator.c:355-356, :448-449), converted from the chain's log-scale working point.
  */
 int emub_estimate_thetas(emub_model *model, const double *ranges, const emub_estimate_opts *opts,
                          double *thetas_out, double *best_lhood, emub_estimate_stats *stats);

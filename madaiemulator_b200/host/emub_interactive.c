@@ -24,7 +24,7 @@ struct emub_multi_emulator {
 
 int emub_multi_emulator_from_snapshot(emub_ctx *ctx, const emub_snapshot *s, emub_multi_emulator **out)
 {
-	if (!ctx || !s || !out) return EMUB_EINVAL;
+	if (!ctx || !s || !out || s->nr < 1 || s->nt < 1) return EMUB_EINVAL;
 	const int n = s->nmodel_points, d = s->nparams, nr = s->nr, nt = s->nt;
 	emub_multi_emulator *me = (emub_multi_emulator *)calloc(1, sizeof(*me));
 	me->nt = nt; me->nr = nr; me->d = d;
@@ -32,6 +32,9 @@ int emub_multi_emulator_from_snapshot(emub_ctx *ctx, const emub_snapshot *s, emu
 	const emub_snapshot_component *c0 = &s->components[0];
 	int rc = emub_model_create(ctx, c0->xmodel, d, n, d, c0->training_vector, c0->cov_fn_index, c0->regression_order, 1, &me->model);
 	if (rc != EMUB_OK) { free(me); return rc; }
+	/* emub_emulator_create_comp copies nthetas(kernel) values out of every component's thetas */
+	for (int c = 0; c < nr; c++)
+		if (s->components[c].nthetas != emub_model_nthetas(me->model)) { emub_model_destroy(me->model); free(me); return EMUB_EINVAL; }
 	double *Y = (double *)malloc(sizeof(double) * (size_t)n * nr);
 	for (int c = 0; c < nr; c++)
 		for (int i = 0; i < n; i++) Y[(size_t)i * nr + c] = s->components[c].training_vector[i];
@@ -138,6 +141,7 @@ int emub_multi_emulator_predict(emub_multi_emulator *me, const double *pts, int 
 	if (G == 1 || m < 2 * G) return predict_one(me, pts, m, pca_output, mean, var);
 	shard_job jobs[64];
 	pthread_t th[64];
+	int started[64];
 	const int base = m / G, rem = m % G;
 	int lo = 0;
 	for (int g = 0; g < G; g++) {
@@ -146,10 +150,14 @@ int emub_multi_emulator_predict(emub_multi_emulator *me, const double *pts, int 
 		jobs[g].pts = pts + (size_t)lo * me->d; jobs[g].m = cnt; jobs[g].pca = pca_output;
 		jobs[g].mean = mean + (size_t)lo * me->nt; jobs[g].var = var + (size_t)lo * me->nt; jobs[g].rc = EMUB_OK;
 		lo += cnt;
-		pthread_create(&th[g], NULL, shard_main, &jobs[g]);
+		started[g] = g > 0 && pthread_create(&th[g], NULL, shard_main, &jobs[g]) == 0;
 	}
 	int rc = EMUB_OK;
-	for (int g = 0; g < G; g++) { pthread_join(th[g], NULL); if (jobs[g].rc != EMUB_OK) rc = jobs[g].rc; }
+	for (int g = 0; g < G; g++) {
+		if (started[g]) pthread_join(th[g], NULL);
+		else shard_main(&jobs[g]); /* share 0, and any share whose thread could not be created, on the caller's thread */
+		if (jobs[g].rc != EMUB_OK) rc = jobs[g].rc;
+	}
 	return rc;
 }
 
@@ -269,7 +277,9 @@ static void parse_convert(void *arg, int s)
 		if (!emub_fast_strtod(p, q, &v)) { /* plain decimal tokens take the exact fast conversion, the rest strtod */
 			char *stop;
 			v = strtod(p, &stop);
-			if (stop == p) { j->bad[s] = g; break; } /* not a number: the reference's fscanf stops here too */
+			/* not a number, or a number with a tail ("1.5abc"): the reference's fscanf("%lf%*c") takes 1.5, eats one
+			 * character and stops the stream at the next conversion; here the stream ends at the token */
+			if (stop != q) { j->bad[s] = g; break; }
 		}
 		j->out[g++] = v;
 		p = q;
@@ -372,6 +382,13 @@ static void slot_wait(stream_pipe *sp, stream_slot *s, int state)
 	while (s->state != state) pthread_cond_wait(&sp->cv, &sp->mu);
 	pthread_mutex_unlock(&sp->mu);
 }
+static int pipe_ok(stream_pipe *sp)
+{
+	pthread_mutex_lock(&sp->mu);
+	const int ok = sp->rc == EMUB_OK;
+	pthread_mutex_unlock(&sp->mu);
+	return ok;
+}
 static void slot_set(stream_pipe *sp, stream_slot *s, int state)
 {
 	pthread_mutex_lock(&sp->mu);
@@ -388,7 +405,7 @@ static void *device_stage(void *arg)
 		double t0 = now_s();
 		slot_wait(sp, s, SLOT_PARSED);
 		sp->t_device_wait += now_s() - t0;
-		if (s->m > 0 && sp->rc == EMUB_OK) {
+		if (s->m > 0 && pipe_ok(sp)) {
 			t0 = now_s();
 			const int rc = emub_multi_emulator_predict(sp->me, s->pts, s->m, sp->pca_output, s->mean, s->var);
 			sp->t_predict += now_s() - t0;
@@ -417,7 +434,7 @@ static void *writer_stage(void *arg)
 		double t0 = now_s();
 		slot_wait(sp, s, SLOT_PREDICTED);
 		sp->t_writer_wait += now_s() - t0;
-		if (s->m > 0 && sp->rc == EMUB_OK) {
+		if (s->m > 0 && pipe_ok(sp)) {
 			t0 = now_s();
 			if (sp->binary) {
 				const size_t cnt = (size_t)s->m * nt;
@@ -445,6 +462,13 @@ static void *writer_stage(void *arg)
 	for (int p = 0; p < 64; p++) free(fj.buf[p]);
 	free(inter);
 	return NULL;
+}
+
+static void stream_pipe_free(stream_pipe *sp)
+{
+	for (int i = 0; i < NSLOT; i++) { free(sp->slot[i].pts); free(sp->slot[i].mean); free(sp->slot[i].var); }
+	pthread_mutex_destroy(&sp->mu);
+	pthread_cond_destroy(&sp->cv);
 }
 
 int emub_interactive_stream(emub_multi_emulator *me, FILE *in, FILE *out, int quiet, int pca_output, int binary,
@@ -478,8 +502,18 @@ int emub_interactive_stream(emub_multi_emulator *me, FILE *in, FILE *out, int qu
 		sp.slot[i].var = (double *)malloc(sizeof(double) * (size_t)block_points * nt);
 	}
 	pthread_t dev_th, wr_th;
-	pthread_create(&dev_th, NULL, device_stage, &sp);
-	pthread_create(&wr_th, NULL, writer_stage, &sp);
+	if (pthread_create(&dev_th, NULL, device_stage, &sp) != 0) {
+		stream_pipe_free(&sp);
+		return EMUB_ENOMEM;
+	}
+	if (pthread_create(&wr_th, NULL, writer_stage, &sp) != 0) {
+		/* let the device stage run out on an empty last block, then give up */
+		sp.slot[0].m = 0; sp.slot[0].last = 1;
+		slot_set(&sp, &sp.slot[0], SLOT_PARSED);
+		pthread_join(dev_th, NULL);
+		stream_pipe_free(&sp);
+		return EMUB_ENOMEM;
+	}
 
 	size_t ibuf_cap = maxvals * 24; /* about one block of "%.17g" text */
 	if (ibuf_cap < ((size_t)1 << 20)) ibuf_cap = (size_t)1 << 20;
@@ -565,10 +599,8 @@ int emub_interactive_stream(emub_multi_emulator *me, FILE *in, FILE *out, int qu
 	}
 	pthread_join(dev_th, NULL);
 	pthread_join(wr_th, NULL);
-	for (int i = 0; i < NSLOT; i++) { free(sp.slot[i].pts); free(sp.slot[i].mean); free(sp.slot[i].var); }
 	free(ibuf);
-	pthread_mutex_destroy(&sp.mu);
-	pthread_cond_destroy(&sp.cv);
+	stream_pipe_free(&sp);
 	if (getenv("EMUB_STREAM_STATS"))
 		fprintf(stderr, "emub_interactive_stream: %lld points, %d io threads | reader: read %.3f s, parse %.3f s, wait %.3f s | device: predict %.3f s, "
 		        "wait %.3f s | writer: format %.3f s, write %.3f s, wait %.3f s\n", sp.total, sp.threads, sp.t_read, sp.t_parse,

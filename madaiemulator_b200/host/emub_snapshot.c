@@ -62,6 +62,7 @@ emub_snapshot *emub_snapshot_load(FILE *f, char *err, int errlen)
 	s->pca_evecs_r = read_doubles(&t, nt * nr);
 	s->pca_zmatrix = read_doubles(&t, n * nr);
 	s->components = (emub_snapshot_component *)calloc(nr, sizeof(emub_snapshot_component));
+	const char *inconsistent = NULL;
 	for (size_t c = 0; c < nr && !t.bad; c++) {
 		emub_snapshot_component *m = &s->components[c];
 		m->nthetas = next_int(&t); m->nparams = next_int(&t); m->nmodel_points = next_int(&t);
@@ -72,6 +73,27 @@ emub_snapshot *emub_snapshot_load(FILE *f, char *err, int errlen)
 			t.bad = 1;
 			break;
 		}
+		/* The engine copies nthetas(kernel) values out of `thetas` and configures ONE model from component 0, so the
+		 * block must agree with both.  Kernel and order are read the way the reference's loader does
+		 * (set_global_ptrs, modelstruct.c:214-258: anything but MATERN32/52 is the power-exponential kernel, anything
+		 * but 1..3 the trivial regression). */
+		{
+			const int kern = (m->cov_fn_index == 2 || m->cov_fn_index == 3) ? m->cov_fn_index : 1;
+			const int ord = (m->regression_order >= 1 && m->regression_order <= 3) ? m->regression_order : 0;
+			const emub_snapshot_component *m0 = &s->components[0];
+			const int kern0 = (m0->cov_fn_index == 2 || m0->cov_fn_index == 3) ? m0->cov_fn_index : 1;
+			const int ord0 = (m0->regression_order >= 1 && m0->regression_order <= 3) ? m0->regression_order : 0;
+			if (m->nthetas != (kern == 1 ? s->nparams + 2 : 3)) { /* modelstruct.c:301-308 */
+				inconsistent = "snapshot component: nthetas does not match its covariance function";
+				t.bad = 1;
+				break;
+			}
+			if (kern != kern0 || ord != ord0) {
+				inconsistent = "snapshot components disagree on covariance function or regression order";
+				t.bad = 1;
+				break;
+			}
+		}
 		m->grad_ranges = read_doubles(&t, 2 * (size_t)m->nthetas);
 		m->xmodel = read_doubles(&t, n * d);
 		m->training_vector = read_doubles(&t, n);
@@ -80,7 +102,7 @@ emub_snapshot *emub_snapshot_load(FILE *f, char *err, int errlen)
 	}
 	free(buf);
 	if (t.bad) {
-		seterr(err, errlen, "snapshot body is truncated or malformed");
+		seterr(err, errlen, inconsistent ? inconsistent : "snapshot body is truncated or malformed");
 		emub_snapshot_free(s);
 		return NULL;
 	}

@@ -161,6 +161,59 @@ def test_factor_internals(ctx):
     m.close()
 
 
+def test_value_only_path_skips_the_inverse_and_returns_the_same_bits(ctx):
+    """evalFnMulti alone (maxmultimin.c:288-394) needs the factor, not the inverse: want_grad = 0 skips the merges of
+    the right spine of the recursion, W^T W and the gradient reduction, and returns bit-identical -L / sigma^2 (both
+    paths solve L u = [y|H] by the same block forward substitution)."""
+    from madaiemulator_b200 import engine
+    for n, d, order in ((700, 5, 1), (1300, 3, 2), (128, 2, 0), (100, 4, 3)):
+        X = ds.synthetic_design(n, d, seed=ds.SEED + 3 * n)
+        y = ds.synthetic_response(X, seed=ds.SEED + 3 * n)
+        m = engine.Model(ctx, X, y, 1, order, max_slots=4)
+        rng = np.random.default_rng(n)
+        ths = np.stack([np.concatenate([[rng.uniform(-5, -2)], rng.uniform(0.0, 1.5, d)]) for _ in range(6)])
+        ctx.profile(True)
+        a = m.loglik_grad_batch(ths, want_grad=False)
+        pa = ctx.profile_read()
+        ctx.profile(True)
+        b = m.loglik_grad_batch(ths, want_grad=True)
+        pb = ctx.profile_read()
+        ctx.profile(False)
+        assert np.array_equal(a["negL"], b["negL"]) and np.array_equal(a["sigma2"], b["sigma2"]) and np.all(a["status"] == 0)
+        assert np.all(a["grad"] == 0.0)
+        assert pa["gemm_lauum"]["launches"] == 0 and pa["grad"]["launches"] == 0
+        assert pb["gemm_lauum"]["launches"] > 0 and pb["grad"]["launches"] > 0
+        if n > 256:
+            assert pa["gemm_trtri"]["work"] < pb["gemm_trtri"]["work"]
+            tot_a = sum(pa[k]["work"] for k in ("gemm_chol", "gemm_trtri", "gemm_lauum"))
+            tot_b = sum(pb[k]["work"] for k in ("gemm_chol", "gemm_trtri", "gemm_lauum"))
+            assert tot_a < 0.55 * tot_b
+        # without the profiler (CUDA-graph replay, several stream groups): still the same bits
+        c = m.loglik_grad_batch(ths, want_grad=False)
+        assert np.array_equal(c["negL"], a["negL"])
+        ref = _oracle(X, y, 1, order).loglik_grad(ths[2], want_grad=False)
+        assert relerr(a["negL"][2], ref["negL"]) < TOL
+        m.close()
+
+
+def test_spd_inverse_of_a_caller_matrix(ctx):
+    """chol_inverse_cov_matrix (emulate-fns.c:275-300) on the engine: inverse and determinant of a host matrix."""
+    from madaiemulator_b200 import engine
+    for n in (50, 128, 333):
+        rng = np.random.default_rng(n)
+        G = rng.normal(size=(n, n))
+        A = G @ G.T / n + np.eye(n)
+        m = engine.Model(ctx, np.zeros((n, 1)), np.zeros(n), 1, 0, max_slots=1)
+        Ainv, logdet = m.spd_inverse(A)
+        ref = np.linalg.inv(A)
+        assert np.max(np.abs(Ainv - ref)) < 1e-11 * np.max(np.abs(ref))
+        assert np.array_equal(Ainv, Ainv.T)
+        assert abs(logdet - np.linalg.slogdet(A)[1]) < 1e-10 * max(1.0, abs(logdet))
+        with pytest.raises(engine.EmubError):
+            m.spd_inverse(A - 3.0 * np.eye(n))
+        m.close()
+
+
 def test_not_positive_definite_reports_edom(ctx):
     """evalFnMulti returns NaN when the Cholesky fails (maxmultimin.c:327-350); the engine flags the
     point and carries on with the rest of the batch."""

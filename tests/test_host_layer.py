@@ -103,6 +103,71 @@ def test_refinement_run_never_lowers_the_likelihood(name):
     ctx.close()
 
 
+@pytest.mark.gpu
+def test_value_policy_does_not_change_the_result():
+    """What the front asks the GPU for when the optimiser wants f alone (value-only at 0.38 n^3, or the gradient
+    speculatively) is a cost decision: the optimiser sees identical bits, so thetas and likelihood are identical."""
+    from madaiemulator_b200 import engine
+    c = load_golden("multi-simple-pc0-o0")
+    ctx = engine.Context(0)
+    m = engine.Model(ctx, c["X"], c["y"], c["kernel"], c["order"], max_slots=16)
+    out = {}
+    for name, pol in (("adaptive", engine.VALUE_ADAPTIVE), ("grad", engine.VALUE_ALWAYS_GRADIENT), ("value", engine.VALUE_ONLY)):
+        out[name] = engine.estimate_thetas(m, max_tries=12, nchains=12, seed=9, value_policy=pol)
+    for name in ("grad", "value"):
+        assert np.array_equal(out[name][0], out["adaptive"][0]) and out[name][1] == out["adaptive"][1]
+    sg, sv, sa = out["grad"][2], out["value"][2], out["adaptive"][2]
+    assert sg["value_evaluations"] == 0 and sg["repeated_points"] == 0 and sg["unused_gradients"] >= 0
+    assert sv["value_evaluations"] > 0 and sv["unused_gradients"] == 0
+    # value-only points the line search accepted were evaluated again: that is the price of the cheap rejections
+    assert sv["evaluations"] == sg["evaluations"] + sv["repeated_points"]
+    assert sg["evaluations"] <= sa["evaluations"] <= sv["evaluations"]
+    m.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_matern_estimate_then_emulate(kernel):
+    """Train-to-predict convention for the Matern kernels: emub_estimate_thetas returns (sigma^2, nugget, log rho) --
+    amplitude and nugget raw, as covariance_fn_matern_three/_five read them (emulator.c:355-356, :448-449) -- so the
+    result can go straight into emub_emulator_create (= alloc_emulator_struct), a snapshot or interactive_mode.  The
+    chains themselves work on (log nugget, log rho) with unit amplitude (deviation D-2)."""
+    from madaiemulator_b200 import engine
+    from oracle.pyoracle import PortOracle
+    n, d, order = 120, 2, 1
+    X = ds.synthetic_design(n, d)
+    y = ds.synthetic_response(X)
+    ctx = engine.Context(0)
+    m = engine.Model(ctx, X, y, kernel, order, max_slots=16)
+    th, best, st = engine.estimate_thetas(m, max_tries=12, nchains=12, seed=5)
+    assert st["rc"] == 0 and st["finite_count"] > 0 and th.shape == (3,)
+    po = PortOracle(X, y, kernel, order)
+    # the working point of the chain: (log nugget, log rho); its likelihood and sigma^2 come back through the oracle
+    work = np.array([np.log(th[1]), th[2]])
+    ref = po.loglik_grad(work, want_grad=False)
+    assert abs(-ref["negL"] - best) <= 1e-9 * max(1.0, abs(best))
+    assert th[0] > 0 and abs(th[0] - ref["sigma2"]) < 1e-6 * ref["sigma2"]
+    assert 0 < th[1] < 1.0   # e^theta_1 with theta_1 in or near [-5, -2] (optstruct.c:153-154), not a log
+    # emulator straight from the estimator's output: positive definite, and the oracle's emulator at the same vector agrees
+    e = m.emulator(th)
+    pts = ds.synthetic_queries(64, d)
+    pts[0] = X[7]
+    mean, var = e.emulate(pts)
+    mr, vr = po.emulator(th).emulate(pts)
+    kappa = th[0] + th[1]
+    assert np.max(np.abs(mean - mr)) < 1e-9 * max(1.0, float(np.max(np.abs(mr))))
+    assert np.max(np.abs(var - vr)) < 1e-9 * max(1.0, kappa)
+    assert abs(mean[0] - y[7]) < 0.5 and np.all(var > -1e-9) and np.all(var < 1.5 * kappa)
+    # refinement run: same convention on the way out
+    th2, best2, _ = engine.estimate_thetas(m, max_tries=12, nchains=12, seed=5, polish_steps=50)
+    assert best2 >= best and th2[0] > 0 and 0 < th2[1] < 1.0
+    m.emulator(th2).close()
+    e.close()
+    m.close()
+    ctx.close()
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (CPU only: the reference's own evalFnGradMulti from oracle/_ref) prints one JSON
     line with the contract's keys."""

@@ -272,6 +272,47 @@ def test_streaming_interactive_mode_matches_reference_cli():
 
 
 @pytest.mark.gpu
+def test_binary_framing():
+    """--binary: the framing the reference's BINARY_INTERACTIVE_MODE switch describes (interactive_emulator.c:119,
+    :418-436): d raw doubles per point in, (mean_i, variance_i) raw doubles per observable out, the text header kept
+    unless --quiet.  The reference's own binary build cannot make a fixture: its loop compares fread's item count (1)
+    with expected_r = sizeof(double) (:391-392, :423) and leaves before the first answer -- checked here by building
+    it.  So the values are compared with the reference CLI's TEXT output for the same points (1e-9), bit for bit
+    with the tool's own text path up to the 17 decimals that path prints, for ragged reads and every block size."""
+    snap = os.path.join(CLI_DIR, "multi-simple-o0.snapshot")
+    nt, d = 6, 3
+    pts = np.array(open(os.path.join(CLI_DIR, "multi-simple.points")).read().split(), dtype=np.float64)
+    raw = pts.tobytes()
+    out = subprocess.run([TOOL, "interactive_mode", snap, "--quiet", "--binary"], input=raw, capture_output=True, check=True, timeout=300).stdout
+    assert len(out) == (len(pts) // d) * 2 * nt * 8
+    got = np.frombuffer(out, dtype=np.float64).reshape(-1, nt, 2)
+    ref = np.array(open(os.path.join(CLI_DIR, "multi-simple-o0.interactive_quiet.txt")).read().split(), dtype=np.float64).reshape(-1, nt, 2)
+    assert np.max(np.abs(got[..., 0] - ref[..., 0]) / np.maximum(1.0, np.abs(ref[..., 0]))) < 1e-9
+    assert np.max(np.abs(got[..., 1] - ref[..., 1])) < 1e-9 * max(1.0, np.max(np.abs(ref[..., 1])))
+    text = subprocess.run([TOOL, "interactive_mode", snap, "--quiet"], input=open(os.path.join(CLI_DIR, "multi-simple.points"), "rb").read(),
+                          capture_output=True, check=True, timeout=300).stdout.decode()
+    assert text == "".join("%.17f\n" % v for v in got.ravel())
+    # block size does not change a bit; a trailing partial point (fewer than d doubles) is dropped like the reference's
+    # short fread (:423-424)
+    small = subprocess.run([TOOL, "interactive_mode", snap, "--quiet", "--binary", "--block", "7"], input=raw + b"\x00" * 12,
+                           capture_output=True, check=True, timeout=300).stdout
+    assert small == out
+    # with the header: text lines first (interactive_emulator.c:398-414), then raw doubles
+    full = subprocess.run([TOOL, "interactive_mode", snap, "--binary"], input=raw[:3 * d * 8], capture_output=True, check=True, timeout=300).stdout
+    header = "".join(["%d\n" % d] + ["param_%d\n" % i for i in range(d)] + ["%d\n" % (2 * nt)] +
+                     ["mean_%d\nvariance_%d\n" % (i, i) for i in range(nt)]).encode()
+    assert full[:len(header)] == header
+    assert full[len(header):] == out[:3 * 2 * nt * 8]
+    # pca_output: first nr entries of each row as in the text protocol
+    pca = subprocess.run([TOOL, "interactive_mode", snap, "--pca_output", "--binary"], input=raw, capture_output=True, check=True, timeout=300).stdout
+    gp = np.frombuffer(pca, dtype=np.float64).reshape(-1, nt, 2)[:, :5]
+    rp = np.array(open(os.path.join(CLI_DIR, "multi-simple-o0.interactive_pca.txt")).read().split(), dtype=np.float64).reshape(-1, nt, 2)[:, :5]
+    assert np.max(np.abs(gp - rp)) < 1e-9 * max(1.0, np.max(np.abs(rp)))
+    # empty input
+    assert subprocess.run([TOOL, "interactive_mode", snap, "--quiet", "--binary"], input=b"", capture_output=True, check=True, timeout=300).stdout == b""
+
+
+@pytest.mark.gpu
 def test_request_response_client_is_served_point_by_point():
     """A client that writes one point and waits for its 2*nt answer lines (the reference flushes per point) must not
     dead-lock on the block reader."""
