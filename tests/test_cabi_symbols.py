@@ -67,7 +67,8 @@ def test_glue_libraries_define_the_reference_symbols():
         return {ln.split()[2]: ln.split()[1] for ln in out if len(ln.split()) == 3}
 
     hot = ["evalFnMulti", "gradFnMulti", "evalFnGradMulti", "estimateSigmaFull", "estimate_thetas_threaded", "alloc_emulator_struct",
-           "free_emulator_struct", "emulate_point", "makeCovMatrix_fnptr", "emulateAtPointList", "emulateAtPoint"]
+           "free_emulator_struct", "emulate_point", "makeCovMatrix_fnptr", "emulateAtPointList", "emulateAtPoint",
+           "makeCovMatrix", "makeKVector_fnptr", "makeKVector", "emulateQuick", "chol_inverse_cov_matrix"]
     mv = ["estimate_multi", "alloc_multi_emulator", "free_multi_emulator", "emulate_point_multi", "emulate_point_multi_pca"]
     b, m = defined(base), defined(multi)
     for name in hot:

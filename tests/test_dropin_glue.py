@@ -305,3 +305,30 @@ def test_batched_front_doors_shard_over_two_gpus(tmp_path):
         outs.append((snap.read_bytes(), ans))
     assert outs[0][0] == outs[1][0]
     assert outs[0][1] == outs[1][1]
+
+
+def test_glue_model_cache_is_bounded(oracles):
+    """Every engine model keeps EMUB_SLOTS factorisation slots on the device; a caller that walks over many
+    modelstructs (the per-component loop of estimate_multi, the R entry points) must not accumulate them: the glue
+    keeps at most EMUB_GLUE_MODELS (default 8), least recently used first out, and a revisited model is rebuilt."""
+    po = oracles
+    po.DropinOracle.reset()
+    L = po.DropinOracle.lib()
+    c = load_golden("uni-simple-o1")
+    th = c["theta_less_amp"]
+    models = [po.DropinOracle(c["X"], (1.0 + 0.1 * k) * c["y"], c["kernel"], c["order"]) for k in range(12)]
+    first = [m.sigma_full(th) for m in models]
+    assert L.libemu_glue_model_count() <= 8
+    again = [m.sigma_full(th) for m in models]
+    assert first == again
+    ref = po.RefOracle(c["X"], 1.3 * c["y"], c["kernel"], c["order"])
+    assert relerr(first[3], ref.sigma_full(th)) < 1e-9
+    # a model with a live emulator_struct is pinned while the others come and go
+    e = models[0].emulator(c["theta_full"])
+    m0, v0 = e.emulate(c["pts"][:5])
+    for m in models[1:]:
+        m.sigma_full(th)
+    m1, v1 = e.emulate(c["pts"][:5])
+    assert np.array_equal(m0, m1) and np.array_equal(v0, v1)
+    del e, models
+    po.DropinOracle.reset()

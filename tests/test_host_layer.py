@@ -117,7 +117,8 @@ def test_value_policy_does_not_change_the_result():
     for name in ("grad", "value"):
         assert np.array_equal(out[name][0], out["adaptive"][0]) and out[name][1] == out["adaptive"][1]
     sg, sv, sa = out["grad"][2], out["value"][2], out["adaptive"][2]
-    assert sg["value_evaluations"] == 0 and sg["repeated_points"] == 0 and sg["unused_gradients"] >= 0
+    # "always gradient": the only value-only points are the scoring evaluations at the end of a restart (maxmultimin.c:103)
+    assert sg["value_evaluations"] <= 12 and sg["repeated_points"] == 0 and sg["unused_gradients"] >= 0
     assert sv["value_evaluations"] > 0 and sv["unused_gradients"] == 0
     # value-only points the line search accepted were evaluated again: that is the price of the cheap rejections
     assert sv["evaluations"] == sg["evaluations"] + sv["repeated_points"]
