@@ -177,7 +177,9 @@ def test_bench_reference_arm_contract():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    # small sample sizes keep the CPU suite short; the default run measures n=1024 and n=2048
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sizes", "256,512"],
                          capture_output=True, check=True, timeout=600).stdout.decode().strip().split("\n")[-1]
     d = json.loads(out)
     assert d["impl"] == "reference" and d["metric"] == "loglik_grad_evals_per_s" and d["unit"] == "evals/s"
@@ -185,3 +187,4 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["n"] == 4096 and d["config"]["d"] == 10
+    assert [x["n"] for x in d["cpu_baseline"]["samples"]] == [256, 512] and d["cpu_baseline"]["fitted_exponent"] is not None
