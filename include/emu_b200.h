@@ -157,6 +157,8 @@ long long emub_launch_count(emub_ctx *ctx);
 int emub_debug_fetch(emub_model *m, int b, int which, double *out, int ldo);
 /* the device exp used by the covariance / gradient kernels (x <= 0), for accuracy tests */
 int emub_debug_exp(emub_ctx *ctx, const double *x, int n, double *out);
+/* the pre-scaled variant the power-exponential kernels use (argument in units of ln2/64, replicated table): e^x */
+int emub_debug_exp_scaled(emub_ctx *ctx, const double *x, int n, double *out);
 /* factor only: runs covariance + Cholesky at theta-less-amp and returns L (lower, n x n) */
 int emub_debug_cholesky(emub_model *m, const double *theta_less_amp, double *L, int ldl, double *logdet);
 

@@ -190,13 +190,16 @@ static emub_model *glue_model_get(const gsl_matrix *x, const gsl_vector *y, int 
 	return m;
 }
 
-/* the engine model that belongs to a reference modelstruct */
-static emub_model *glue_model_for(modelstruct *ms)
+/* the engine model that belongs to a reference modelstruct.  o: the optstruct the caller was handed next to the model
+ * (the R entry points build their modelstruct with alloc_modelstruct, which leaves the_model->options NULL,
+ * modelstruct.c:12-19), else the model's own */
+static emub_model *glue_model_for_opts(modelstruct *ms, optstruct *o)
 {
-	optstruct *o = ms->options;
+	if (!o) o = ms->options;
 	return glue_model_get(ms->xmodel, ms->training_vector, o->nmodel_points, o->nparams, o->cov_fn_index, o->regression_order,
 	                      env_int("EMUB_SLOTS", 8));
 }
+static emub_model *glue_model_for(modelstruct *ms) { return glue_model_for_opts(ms, NULL); }
 
 static int glue_kernel_of(double (*fn)(gsl_vector *, gsl_vector *, gsl_vector *, int, int))
 {
@@ -233,7 +236,7 @@ static int glue_eval(const gsl_vector *theta_vec, void *params_in, int want_grad
 	int status = 0;
 	for (size_t i = 0; i < theta_vec->size; i++) th[i] = gsl_vector_get(theta_vec, i);
 	pthread_mutex_lock(&g_call_mu);
-	emub_model *m = glue_model_for(p->the_model);
+	emub_model *m = glue_model_for_opts(p->the_model, p->options);
 	const int rc = emub_loglik_grad_batch(m, th, 1, want_grad, negL, grad, sigma2, &status);
 	pthread_mutex_unlock(&g_call_mu);
 	if (rc != EMUB_OK) glue_die("emub_loglik_grad_batch");
@@ -281,7 +284,7 @@ double estimateSigmaFull(gsl_vector *thetas, void *params_in)
 void estimate_thetas_threaded(modelstruct *the_model, optstruct *options)
 {
 	pthread_mutex_lock(&g_call_mu);
-	emub_model *m = glue_model_for(the_model);
+	emub_model *m = glue_model_for_opts(the_model, options);
 	const int nth = options->nthetas;
 	long ncpus = sysconf(_SC_NPROCESSORS_ONLN);
 	emub_estimate_opts o;
@@ -386,7 +389,7 @@ void emulateAtPointList(modelstruct *the_model, gsl_matrix *point_list, optstruc
 	for (int i = 0; i < options->nthetas; i++) th[i] = gsl_vector_get(the_model->thetas, i);
 	emub_emulator *eh = NULL;
 	pthread_mutex_lock(&g_call_mu);
-	emub_model *m = glue_model_for(the_model);
+	emub_model *m = glue_model_for_opts(the_model, options);
 	if (emub_emulator_create(m, th, &eh) != EMUB_OK) { /* chol_inverse_cov_matrix exits on a failed factorisation, :282-285 */
 		fprintf(stderr, "emulateAtPointList: %s\n", emub_last_error());
 		exit(EXIT_FAILURE);
@@ -399,11 +402,12 @@ void emulateAtPointList(modelstruct *the_model, gsl_matrix *point_list, optstruc
 
 /* the emulator of (model, thetas), kept between calls: what struct emulateMCData's host-side C^-1 is to the reference's
  * Monte-Carlo fast path (rbind.c:299-425).  g_call_mu held. */
-static emub_emulator *glue_quick_emulator(modelstruct *the_model, int nth)
+static emub_emulator *glue_quick_emulator(modelstruct *the_model, optstruct *options)
 {
 	double th[GLUE_TH];
+	const int nth = options->nthetas;
 	for (int i = 0; i < nth; i++) th[i] = gsl_vector_get(the_model->thetas, i);
-	emub_model *m = glue_model_for(the_model);
+	emub_model *m = glue_model_for_opts(the_model, options);
 	pthread_mutex_lock(&g_mu);
 	for (int k = 0; k < g_nquick; k++)
 		if (g_quick[k].m == m && g_quick[k].nth == nth && memcmp(g_quick[k].th, th, sizeof(double) * (size_t)nth) == 0) {
@@ -439,7 +443,7 @@ void emulateAtPoint(modelstruct *the_model, gsl_vector *the_point, optstruct *op
 	double x[GLUE_TH];
 	for (int i = 0; i < options->nparams; i++) x[i] = gsl_vector_get(the_point, i);
 	pthread_mutex_lock(&g_call_mu);
-	emub_emulator *eh = glue_quick_emulator(the_model, options->nthetas);
+	emub_emulator *eh = glue_quick_emulator(the_model, options);
 	const int rc = emub_predict_few(eh, x, options->nparams, 1, the_mean, the_variance);
 	pthread_mutex_unlock(&g_call_mu);
 	if (rc != EMUB_OK) glue_die("emub_predict_few");

@@ -955,6 +955,23 @@ extern "C" int emub_debug_exp(emub_ctx *c, const double *x, int n, double *out)
 	return EMUB_OK;
 }
 
+extern "C" int emub_debug_exp_scaled(emub_ctx *c, const double *x, int n, double *out)
+{
+	if (!c || !x || !out || n < 1) return set_err(EMUB_EINVAL, "emub_debug_exp_scaled: bad argument%s");
+	CUDA_TRY(cudaSetDevice(c->device));
+	ScopedDev sx, sout;
+	CUDA_TRY(sx.alloc((size_t)n));
+	CUDA_TRY(sout.alloc((size_t)n));
+	CUDA_TRY(cudaMemcpy(sx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+	{
+		LaunchScope ls(c, EMUB_K_SMALL, 0, c->streams[0]);
+		k_debug_exp_scaled<<<(n + 255) / 256, 256, 0, c->streams[0]>>>(sx.p, n, sout.p);
+	}
+	CUDA_TRY(cudaStreamSynchronize(c->streams[0]));
+	CUDA_TRY(cudaMemcpy(out, sout.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+	return EMUB_OK;
+}
+
 extern "C" int emub_debug_cholesky(emub_model *m, const double *theta_less_amp, double *L, int ldl, double *logdet)
 {
 	if (!m || !theta_less_amp || !L || ldl < m->n) return set_err(EMUB_EINVAL, "emub_debug_cholesky: bad argument%s");

@@ -79,13 +79,13 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 	double *sXi = sm;            // [d][64]
 	double *sXj = sm + d * CT;   // [d][64]
 	__shared__ double sc[CONST_STRIDE];
-	__shared__ double sh[MAXD];  // -0.5 / l_k^2 (scaling by 1/2 is exact: same bits as the literal (-1/2 dist) dist / l^2 up to D-5)
+	__shared__ double sh[MAXD];  // (-0.5 / l_k^2) * 64/ln2: the literal (-1/2 dist) dist / l^2 (scaling by 1/2 is exact; D-5) in exp_scaled's units
 	__shared__ double stab[64 * EXP_REP];
 	exp_table_load<EXP_REP>(stab);
 	const int tid = threadIdx.x;
 	const double *cg = consts + b * const_stride;
 	for (int i = tid; i < 4 + 3 * d; i += 256) sc[i] = cg[i];
-	if (KERNEL == 1) for (int i = tid; i < d; i += 256) sh[i] = -0.5 * cg[4 + i];
+	if (KERNEL == 1) for (int i = tid; i < d; i += 256) sh[i] = (-0.5 * cg[4 + i]) * EXP_SCALE;  // exponent in units of ln2/64 (exp_scaled)
 	const int i0 = bi * CT, j0 = bj * CT;
 	const int ncols = CROSS ? mq : n;
 	const double *XJ = CROSS ? Q : X;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 			double v;
 			if (gi < n && gj < ncols) {
 				if (KERNEL == 1) {
-					v = exp_neg<EXP_REP>(e[r][c], stab) * sc[0];  // emulator.c:134
+					v = exp_scaled<EXP_REP>(e[r][c], stab) * sc[0];  // emulator.c:134
 				} else {
 					// emulator.c:344-386 (Matern 3/2), :438-480 (Matern 5/2); e holds the squared distance
 					const double dist = sqrt(e[r][c]);
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 		}
 	} else if (KERNEL == 1) {
 		for (int k = 0; k < d; k++) {
-			const double ak = sc[4 + d + k];
+			const double akz = -sc[4 + d + k] * EXP_SCALE;  // -a_k in exp_scaled's units
 			double s = 0.0;
 #pragma unroll
 			for (int r = 0; r < 4; r++) {
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 				for (int c = 0; c < 4; c++) {
 					const double dl = xi - sXj[k * CT + tx + 16 * c];
 					const double q = dl * dl;
-					s += w[r][c] * (q * exp_neg<EXP_REP>(-ak * q, stab));
+					s += w[r][c] * (q * exp_scaled<EXP_REP>(akz * q, stab));
 				}
 			}
 #pragma unroll
@@ -650,6 +650,16 @@ __global__ void k_debug_exp(const double *__restrict__ x, int n, double *__restr
 	__syncthreads();
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) out[i] = exp_neg(x[i], stab);
+}
+
+// test hook: exp_scaled with the replicated table, z = x * 64 / ln 2 formed on the device like the kernels do
+__global__ void k_debug_exp_scaled(const double *__restrict__ x, int n, double *__restrict__ out)
+{
+	__shared__ double stab[64 * EXP_REP];
+	exp_table_load<EXP_REP>(stab);
+	__syncthreads();
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = exp_scaled<EXP_REP>(x[i] * EXP_SCALE, stab);
 }
 
 // pack results for the device-pointer API: out[b] = (negL, sigma2, status, logdet, grad[nth1])

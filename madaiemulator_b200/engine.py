@@ -35,7 +35,7 @@ SYMBOLS = [
     "emub_ctx_synchronize", "emub_loglik_extras", "emub_emulator_create", "emub_emulator_destroy",
     "emub_emulator_beta", "emub_predict_batch", "emub_predict_few", "emub_predict_batch_dev", "emub_profile_enable",
     "emub_profile_reset", "emub_profile_read", "emub_profile_name", "emub_launch_count", "emub_debug_fetch",
-    "emub_debug_cholesky", "emub_debug_exp",
+    "emub_debug_cholesky", "emub_debug_exp", "emub_debug_exp_scaled",
 ]
 
 
@@ -107,6 +107,7 @@ def lib():
     L.emub_debug_fetch.argtypes = [_vp, _ci, _ci, _dp, _ci]
     L.emub_debug_cholesky.argtypes = [_vp, _dp, _dp, _ci, _dp]
     L.emub_debug_exp.argtypes = [_vp, _dp, _ci, _dp]
+    L.emub_debug_exp_scaled.argtypes = [_vp, _dp, _ci, _dp]
     _lib = L
     return L
 
@@ -152,6 +153,12 @@ class Context:
         x = _c(x).ravel()
         out = np.empty_like(x)
         _check(self.L.emub_debug_exp(self.h, _P(x), x.size, _P(out)))
+        return out
+
+    def debug_exp_scaled(self, x):
+        x = _c(x).ravel()
+        out = np.empty_like(x)
+        _check(self.L.emub_debug_exp_scaled(self.h, _P(x), x.size, _P(out)))
         return out
 
     def launch_count(self):

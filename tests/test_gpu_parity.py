@@ -312,6 +312,14 @@ def test_device_exp(ctx):
     ulps = np.abs(got[live] - ref[live]) / np.spacing(ref[live])
     assert ulps.max() < 2.0
     assert np.all(got[~live] == 0.0)
+    # exp_scaled (power-exponential covariance / gradient kernels): the argument is formed as x * 64/ln2 in FP64, so it
+    # carries |x| * 2^-53 of rounding on top of the 2 ulp of the evaluation
+    got2 = ctx.debug_exp_scaled(x)
+    rel = np.abs(got2[live] - ref[live]) / ref[live]
+    assert np.all(rel < 2.5e-16 * (2.0 + np.abs(x[live])))
+    small = live & (x > -1.0)
+    assert (np.abs(got2[small] - ref[small]) / np.spacing(ref[small])).max() < 2.5
+    assert np.all(got2[x < -709.0] == 0.0)
 
 
 def test_cfg3_matern52_batched_restarts(ctx):
