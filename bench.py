@@ -525,6 +525,7 @@ def main():
         step_dev()
         ctx.synchronize()
         prof = ctx.profile_read()
+        ctx.profile(True)  # resets the accumulators
         emu.emulate_dev(d_pts.data_ptr(), min(mq, 16384), d_mean.data_ptr(), d_var.data_ptr())
         ctx.synchronize()
         prof_pred = ctx.profile_read()

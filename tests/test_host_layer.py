@@ -157,8 +157,11 @@ def test_matern_estimate_then_emulate(kernel):
     mean, var = e.emulate(pts)
     mr, vr = po.emulator(th).emulate(pts)
     kappa = th[0] + th[1]
-    assert np.max(np.abs(mean - mr)) < 1e-9 * max(1.0, float(np.max(np.abs(mr))))
-    assert np.max(np.abs(var - vr)) < 1e-9 * max(1.0, kappa)
+    # the optimum sits at a long correlation length where C is ill conditioned: two correct FP64 evaluations of the
+    # cancellation kappa - k^T C^-1 k agree to ~cond(C) * eps, not 1e-9 (the fixed-theta parity tests hold the 1e-9 bar)
+    tol = max(1e-9, 4.0 * np.finfo(float).eps * np.linalg.cond(po.cov_matrix(th)))
+    assert np.max(np.abs(mean - mr)) < tol * max(1.0, float(np.max(np.abs(mr))))
+    assert np.max(np.abs(var - vr)) < tol * max(1.0, kappa)
     assert abs(mean[0] - y[7]) < 0.5 and np.all(var > -1e-9) and np.all(var < 1.5 * kappa)
     # refinement run: same convention on the way out
     th2, best2, _ = engine.estimate_thetas(m, max_tries=12, nchains=12, seed=5, polish_steps=50)
