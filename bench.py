@@ -606,7 +606,7 @@ def main():
                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(B * nth1 * 8),
-                       "d2h_bytes_per_step": int(B * 90 * 8)},
+                       "d2h_bytes_per_step": int(B * engine.RES_STRIDE * 8)},
                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                "failed_points": nfail, "kernels": kernels,
                "extra": {"emulated_points_per_s": {"value": pred_value, "unit": "points/s", "points_per_step_per_gpu": mq,

@@ -194,6 +194,25 @@ extern "C" int emub_ctx_create(int device, emub_ctx **out)
 	CUDA_TRY(cudaFuncSetAttribute(k_gemm<RMAJOR, RMAJOR, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
 	CUDA_TRY(cudaFuncSetAttribute(k_gemm<KMAJOR, RMAJOR, EPI_COLSUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
 	CUDA_TRY(cudaFuncSetAttribute(k_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, POTF2_SMEM_BYTES));
+	// kernels whose dynamic shared memory grows with nparams / nregression_fns past the 48 KB default
+	{
+		const int stage = (2 * MAXD * CT + 2 * CT) * (int)sizeof(double);
+		CUDA_TRY(cudaFuncSetAttribute(k_cov<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_cov<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_cov<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_cov<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_cov<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_cov<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_grad_tiles<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_grad_tiles<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_grad_tiles<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_grad_tiles<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_grad_tiles<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_grad_tiles<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage));
+		CUDA_TRY(cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MAXNCP * (MAXNCP + 1) * (int)sizeof(double)));
+		CUDA_TRY(cudaFuncSetAttribute(k_pred_final, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXNCP * MAXNCP * (int)sizeof(double)));
+		CUDA_TRY(cudaFuncSetAttribute(k_gram_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, TB * MAXNCP * (int)sizeof(double)));
+	}
 	*out = c;
 	return EMUB_OK;
 }
@@ -322,11 +341,11 @@ extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n,
                                  int order, int max_slots, emub_model **out)
 {
 	if (!ctx || !X || !y || !out) return set_err(EMUB_EINVAL, "emub_model_create: null argument%s");
-	if (n < 1 || d < 1 || d > MAXD || ldx < d) return set_err(EMUB_EINVAL, "emub_model_create: need 1 <= d <= 32, n >= 1%s");
+	if (n < 1 || d < 1 || d > MAXD || ldx < d) return set_err(EMUB_EINVAL, "emub_model_create: need 1 <= nparams <= 64, n >= 1%s");
 	if (kernel < 1 || kernel > 3) kernel = EMUB_POWEREXP;  // multi_modelstruct.c:67-74 falls back to power-exp
 	if (order < 0 || order > 3) order = 0;
 	const int p = regression_fns(order, d);
-	if (p + 1 > MAXNCP) return set_err(EMUB_EINVAL, "emub_model_create: 1 + order*d + 1 must be <= 48%s");
+	if (p + 1 > MAXNCP) return set_err(EMUB_EINVAL, "emub_model_create: 1 + regression_order * nparams + 1 must be <= 104%s");
 	CUDA_TRY(cudaSetDevice(ctx->device));
 	emub_model *m = new emub_model();  // value-initialised: every pointer starts out null, so a failed set-up can be torn down
 	m->ctx = ctx; m->n = n; m->d = d; m->p = p; m->kernel = kernel; m->order = order;
@@ -377,10 +396,10 @@ extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n,
 	MODEL_TRY(cudaMalloc(&m->dAB, S * m->npad * m->ncp * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dConsts, S * CONST_STRIDE * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dLogdet, S * m->nblk * sizeof(double)));
-	MODEL_TRY(cudaMalloc(&m->dGramPart, S * m->nblk * MAXNCP * MAXNCP * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dGramPart, S * m->nblk * (size_t)m->ncp * m->ncp * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dRes, S * RES_STRIDE * sizeof(double)));
 	const size_t nt64 = m->npad / CT, ntl = nt64 * (nt64 + 1) / 2;
-	MODEL_TRY(cudaMalloc(&m->dGradPart, S * ntl * MAXD * sizeof(double)));
+	MODEL_TRY(cudaMalloc(&m->dGradPart, S * ntl * (size_t)m->d * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dMinv, S * MAXNCP * MAXNCP * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dThetas, S * (MAXD + 2) * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dInfo, S * sizeof(int)));
@@ -613,11 +632,11 @@ static void run_regression(emub_model *m, cudaStream_t st, int s0, int count, in
 	{
 		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
 		k_gram_partial<<<dim3(m->nblk, count), 256, (size_t)TB * m->ncp * sizeof(double), st>>>(
-		    UG, sUG, m->ncp, m->p + 1, m->dGramPart + (size_t)s0 * m->nblk * MAXNCP * MAXNCP, m->nblk);
+		    UG, sUG, m->ncp, m->p + 1, m->dGramPart + (size_t)s0 * m->nblk * m->ncp * m->ncp, m->nblk);
 	}
 	{
 		LaunchScope ls(c, EMUB_K_SMALL, 0, st);
-		k_small<<<count, 256, 0, st>>>(m->dGramPart + (size_t)s0 * m->nblk * MAXNCP * MAXNCP, m->nblk, UG, sUG, m->ncp, m->p, m->n,
+		k_small<<<count, 256, 2 * (size_t)(m->p + 1) * (m->p + 2) * sizeof(double), st>>>(m->dGramPart + (size_t)s0 * m->nblk * m->ncp * m->ncp, m->nblk, UG, sUG, m->ncp, m->p, m->n,
 		                               m->npad, m->dLogdet + (size_t)s0 * m->nblk, m->nblk, m->dInfo + s0,
 		                               m->dRes + (size_t)s0 * RES_STRIDE, m->dConsts + (size_t)s0 * CONST_STRIDE, emulator_mode,
 		                               m->dMinv + (size_t)s0 * MAXNCP * MAXNCP);
@@ -643,7 +662,7 @@ static void run_gradient(emub_model *m, cudaStream_t st, int s0, int count)
 	const size_t smem = (2 * (size_t)m->d * CT + 2 * CT) * sizeof(double);
 	double *Cinv = m->bufA + (size_t)s0 * m->mat;
 	double *AB = m->dAB + (size_t)s0 * sUG;
-	double *part = m->dGradPart + (size_t)s0 * ntl * MAXD;
+	double *part = m->dGradPart + (size_t)s0 * ntl * m->d;
 	const double *consts = m->dConsts + (size_t)s0 * CONST_STRIDE;
 	{
 		LaunchScope ls(c, EMUB_K_GRAD, count * 4.0 * (double)m->mat, st);
@@ -1178,7 +1197,7 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 		}
 		{
 			LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);
-			k_pred_final<<<1, 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, m->npad / FEW_ROWS, ldk, e->beta, e->Minv,
+			k_pred_final<<<1, 128, (size_t)m->p * m->p * sizeof(double), st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, m->npad / FEW_ROWS, ldk, e->beta, e->Minv,
 			                                e->kappa, dMean, dVar, m->npad / FEW_ROWS, (long long)FEW_MAX * m->ncp, nullptr, 0, 0);
 		}
 		CUDA_TRY(cudaGetLastError());
@@ -1195,7 +1214,7 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 	}
 	{
 		LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);
-		k_pred_final<<<(mq + 127) / 128, 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, m->nblk * DefaultCfg::SUBM, ldk, e->beta,
+		k_pred_final<<<(mq + 127) / 128, 128, (size_t)m->p * m->p * sizeof(double), st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, m->nblk * DefaultCfg::SUBM, ldk, e->beta,
 		                                               e->Minv, e->kappa, dMean, dVar, 1, 0, nullptr, 0, 0);
 	}
 	CUDA_TRY(cudaGetLastError());
@@ -1292,7 +1311,7 @@ static int few_set_launch(emub_emulator *const *emus, int nr, cudaStream_t st, c
 	}
 	{
 		LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);
-		k_pred_final<<<dim3(1, nr), 128, 0, st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, nparts, ldk, nullptr, nullptr, 0.0, dMean,
+		k_pred_final<<<dim3(1, nr), 128, (size_t)m->p * m->p * sizeof(double), st>>>(dQ, mq, m->d, m->order, m->p, w->dKA, m->ncp, w->dVsq, nparts, ldk, nullptr, nullptr, 0.0, dMean,
 		                                          dVar, nparts, (long long)FEW_MAX * m->ncp, w->dFewSet, kastride, w->mqc);
 	}
 	CUDA_TRY(cudaGetLastError());

@@ -12,8 +12,8 @@
 
 namespace emub {
 
-constexpr int MAXD = 32;     // nparams limit (smem staging of design rows)
-constexpr int MAXNCP = 48;   // 1 + nregression_fns, padded to a multiple of 8
+constexpr int MAXD = 64;     // nparams limit (smem staging of design rows: 2 * d * 64 doubles per covariance / gradient CTA)
+constexpr int MAXNCP = 104;  // 1 + nregression_fns, padded to a multiple of 8 (cubic regression up to d = 34, linear up to d = 64)
 constexpr int CT = 64;       // covariance / gradient tile edge
 
 // few-points prediction path (k_few_*, k_pred_final): one entry per emulator (PCA component) when several are answered
@@ -303,12 +303,12 @@ __global__ void __launch_bounds__(256) k_gram_partial(const double *__restrict__
 	const double *UG = UGbase + b * strideUG + (size_t)ch * TB * ncp;
 	for (int idx = threadIdx.x; idx < TB * ncp; idx += 256) sm[idx] = UG[idx];
 	__syncthreads();
-	double *o = part + ((size_t)b * nchunks + ch) * (MAXNCP * MAXNCP);
+	double *o = part + ((size_t)b * nchunks + ch) * ((size_t)ncp * ncp);
 	for (int idx = threadIdx.x; idx < nc * nc; idx += 256) {
 		int c1 = idx / nc, c2 = idx - c1 * nc;
 		double s = 0.0;
 		for (int r = 0; r < TB; r++) s += sm[r * ncp + c1] * sm[r * ncp + c2];
-		o[c1 * MAXNCP + c2] = s;
+		o[c1 * ncp + c2] = s;
 	}
 }
 
@@ -342,8 +342,12 @@ __global__ void __launch_bounds__(256) k_small(const double *__restrict__ part, 
                                                const int *__restrict__ info, double *__restrict__ res,
                                                double *__restrict__ consts, int emulator_mode, double *__restrict__ Minv)
 {
-	__shared__ double S[MAXNCP][MAXNCP + 1];
-	__shared__ double Lm[MAXNCP][MAXNCP + 1];
+	// S and Lm: (p + 1) x (p + 2) doubles each, in dynamic shared memory (2 * (p + 1) * (p + 2) doubles)
+	extern __shared__ double sm_small[];
+	const int sld = p + 2;
+	double *S = sm_small, *Lm = sm_small + (size_t)(p + 1) * sld;
+#define S_(i, j) S[(i) * sld + (j)]
+#define L_(i, j) Lm[(i) * sld + (j)]
 	__shared__ double beta[MAXNCP];
 	__shared__ double scratch[8];
 	__shared__ int regbad;
@@ -354,43 +358,43 @@ __global__ void __launch_bounds__(256) k_small(const double *__restrict__ part, 
 	for (int idx = tid; idx < nc * nc; idx += 256) {
 		int c1 = idx / nc, c2 = idx - c1 * nc;
 		double s = 0.0;
-		for (int ch = 0; ch < nchunks; ch++) s += part[((size_t)b * nchunks + ch) * (MAXNCP * MAXNCP) + c1 * MAXNCP + c2];
-		S[c1][c2] = s;
+		for (int ch = 0; ch < nchunks; ch++) s += part[((size_t)b * nchunks + ch) * ((size_t)ncp * ncp) + c1 * ncp + c2];
+		S_(c1, c2) = s;
 	}
 	if (tid == 0) regbad = 0;
 	__syncthreads();
-	// Cholesky of D = S[1..p][1..p] by warp 0 (p <= 47: lanes own rows i and i + 32)
+	// Cholesky of D = S[1..p][1..p] by warp 0 (lanes own rows i, i + 32, ...)
 	if (tid < 32) {
 		for (int i = tid; i < p; i += 32)
-			for (int c = 0; c < p; c++) Lm[i][c] = S[1 + i][1 + c];
+			for (int c = 0; c < p; c++) L_(i, c) = S_(1 + i, 1 + c);
 		__syncwarp();
 		for (int j = 0; j < p; j++) {
-			double djj = Lm[j][j];
+			double djj = L_(j, j);
 			if (!(djj > 0.0)) { if (tid == 0) regbad = 1; djj = 1.0; }
 			double ljj = sqrt(djj);
 			__syncwarp();
 			for (int i = tid; i < p; i += 32) {
-				if (i == j) Lm[j][j] = ljj;
-				else if (i > j) Lm[i][j] = Lm[i][j] / ljj;
+				if (i == j) L_(j, j) = ljj;
+				else if (i > j) L_(i, j) = L_(i, j) / ljj;
 			}
 			__syncwarp();
 			for (int i = j + 1 + tid; i < p; i += 32) {
-				double lij = Lm[i][j];
-				for (int c = j + 1; c <= i; c++) Lm[i][c] -= lij * Lm[c][j];
+				double lij = L_(i, j);
+				for (int c = j + 1; c <= i; c++) L_(i, c) -= lij * L_(c, j);
 			}
 			__syncwarp();
 		}
 		// solve D beta = G^T u  (S[1+i][0])
 		if (tid == 0) {
 			for (int i = 0; i < p; i++) {
-				double s = S[1 + i][0];
-				for (int c = 0; c < i; c++) s -= Lm[i][c] * beta[c];
-				beta[i] = s / Lm[i][i];
+				double s = S_(1 + i, 0);
+				for (int c = 0; c < i; c++) s -= L_(i, c) * beta[c];
+				beta[i] = s / L_(i, i);
 			}
 			for (int i = p - 1; i >= 0; i--) {
 				double s = beta[i];
-				for (int c = i + 1; c < p; c++) s -= Lm[c][i] * beta[c];
-				beta[i] = s / Lm[i][i];
+				for (int c = i + 1; c < p; c++) s -= L_(c, i) * beta[c];
+				beta[i] = s / L_(i, i);
 			}
 		}
 		if (emulator_mode) {
@@ -400,13 +404,13 @@ __global__ void __launch_bounds__(256) k_small(const double *__restrict__ part, 
 				double x[MAXNCP];
 				for (int i = 0; i < p; i++) {
 					double s = (i == c) ? 1.0 : 0.0;
-					for (int k = 0; k < i; k++) s -= Lm[i][k] * x[k];
-					x[i] = s / Lm[i][i];
+					for (int k = 0; k < i; k++) s -= L_(i, k) * x[k];
+					x[i] = s / L_(i, i);
 				}
 				for (int i = p - 1; i >= 0; i--) {
 					double s = x[i];
-					for (int k = i + 1; k < p; k++) s -= Lm[k][i] * x[k];
-					x[i] = s / Lm[i][i];
+					for (int k = i + 1; k < p; k++) s -= L_(k, i) * x[k];
+					x[i] = s / L_(i, i);
 				}
 				for (int i = 0; i < p; i++) Minv[(size_t)b * MAXNCP * MAXNCP + i * MAXNCP + c] = x[i];
 			}
@@ -444,6 +448,8 @@ __global__ void __launch_bounds__(256) k_small(const double *__restrict__ part, 
 		consts[(size_t)b * CONST_STRIDE + 3] = sigma2;
 	}
 }
+#undef S_
+#undef L_
 
 // ---- K4: fused gradient reduction ---------------------------------------------------------------------
 // part[b][tile][k] = sum over strictly-lower pairs (i > j) of the 64 x 64 tile of
@@ -592,7 +598,7 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 		// lower-triangular tile index
 		const size_t tile = (size_t)bi * (bi + 1) / 2 + bj;
 		const size_t ntl = (size_t)ntiles64 * (ntiles64 + 1) / 2;
-		part[((size_t)b * ntl + tile) * MAXD + tid] = s;
+		part[((size_t)b * ntl + tile) * nslots + tid] = s;
 	}
 }
 
@@ -694,7 +700,7 @@ __global__ void __launch_bounds__(128) k_pred_final(const double *__restrict__ Q
 		mean += (size_t)z * mstride;
 		var += (size_t)z * mstride;
 	}
-	__shared__ double sM[MAXNCP * MAXNCP];
+	extern __shared__ double sM[];  // p x p
 	__shared__ double sb[MAXNCP];
 	for (int i = threadIdx.x; i < p * p; i += blockDim.x) sM[i] = Minv[(i / p) * MAXNCP + (i % p)];
 	for (int i = threadIdx.x; i < p; i += blockDim.x) sb[i] = beta[i];

@@ -94,7 +94,9 @@ __device__ __forceinline__ void potf2_diag_block(int q, int lane, const double *
 #pragma unroll
 		for (int j = 0; j < 8; j++) {
 			double pv = a[j][j];
-			const bool ok = (pv > 1.0e-290) && (pv < 1.0e300);
+			// gsl_linalg_cholesky_decomp fails on a pivot <= 0 (GSL_EDOM, maxmultimin.c:325-327); so does this, plus the
+			// pivots the reciprocal square root below cannot take: subnormal (< 2.3e-308), inf or NaN
+			const bool ok = (pv >= 2.2250738585072014e-308) && (pv < 1.0e307);
 			if (!ok) { *s_bad = 1; pv = 1.0; }
 			pivots[q * 8 + j] = pv;
 			const double isq = potf2_rsqrt(pv);

@@ -14,6 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libemub.so")
 
 POWEREXP, MATERN32, MATERN52 = 1, 2, 3
+MAXD, MAXNCP = 64, 104               # nparams / (1 + nregression_fns) limits of the engine (csrc/emub_kernels.cuh)
+RES_STRIDE = 8 + MAXNCP + MAXD + 2   # doubles per point the host-pointer likelihood call reads back
 OK, EDOM, EREG, EINVAL, ECUDA, ENOMEM = 0, 1, 2, 3, 4, 5
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -366,7 +368,7 @@ def predict_multi(emulators, pts, training_mean=None, evecs=None, evals=None, fe
 
 # ---- host C layer (madaiemulator_b200/host/libemuhost.so): restart driver over the batched evaluator ----------
 HOST_LIB_PATH = os.path.join(_HERE, "host", "libemuhost.so")
-HOST_SYMBOLS = ["emub_estimate_default_opts", "emub_sample_scales", "emub_optimization_ranges", "emub_random_init",
+HOST_SYMBOLS = ["emub_estimate_default_opts", "emub_sample_scales", "emub_optimization_ranges", "emub_optimization_ranges_ex", "emub_random_init",
                 "emub_estimate_thetas", "emub_estimate_thetas_from", "emub_estimate_thetas_multi", "emub_estimate_thetas_multi_devices", "emub_estimate_thetas_multi_devices_ranges", "emub_snapshot_load",
                 "emub_snapshot_load_path", "emub_snapshot_free", "emub_multi_emulator_from_snapshot",
                 "emub_multi_emulator_destroy", "emub_multi_emulator_predict", "emub_multi_emulator_predict_few", "emub_interactive_stream", "emub_parse_doubles", "emub_fast_strtod", "emub_fast_format17",
@@ -410,6 +412,8 @@ def host_lib():
     H.emub_sample_scales.restype = None
     H.emub_optimization_ranges.argtypes = [_ci, _dp, _ci, _ci, _ci, _dp]
     H.emub_optimization_ranges.restype = None
+    H.emub_optimization_ranges_ex.argtypes = [_ci, _dp, _ci, _ci, _ci, _ci, _ci, ctypes.c_double, _dp]
+    H.emub_optimization_ranges_ex.restype = None
     H.emub_random_init.argtypes = [ctypes.c_ulonglong, _ci, _dp, _ci, _dp]
     H.emub_random_init.restype = None
     H.emub_estimate_thetas.argtypes = [_vp, _dp, ctypes.POINTER(EstimateOpts), _dp, _dp, ctypes.POINTER(EstimateStats)]
@@ -421,13 +425,15 @@ def host_lib():
     return H
 
 
-def optimization_ranges(kernel, X):
-    """setup_optimization_ranges (optstruct.c:142) on the host: nthetas x 2."""
+def optimization_ranges(kernel, X, use_data_scales=True, fixed_nugget=None):
+    """setup_optimization_ranges (optstruct.c:142) on the host: nthetas x 2.  fixed_nugget: the optstruct's
+    fixed_nugget_mode = 1 with that value (optstruct.c:217-225)."""
     X = _c(X)
     n, d = X.shape
     nth = d + 2 if kernel == POWEREXP else 3
     r = np.empty((nth, 2))
-    host_lib().emub_optimization_ranges(kernel, _P(X), d, n, d, _P(r))
+    host_lib().emub_optimization_ranges_ex(kernel, _P(X), d, n, d, 1 if use_data_scales else 0, 0 if fixed_nugget is None else 1,
+                                           0.0 if fixed_nugget is None else float(fixed_nugget), _P(r))
     return r
 
 

@@ -40,7 +40,8 @@ void emub_sample_scales(const double *X, int ldx, int n, int d, double *scales)
 }
 
 /* optstruct.c:142-226 */
-void emub_optimization_ranges(int kernel, const double *X, int ldx, int n, int d, double *ranges)
+void emub_optimization_ranges_ex(int kernel, const double *X, int ldx, int n, int d, int use_data_scales, int fixed_nugget_mode,
+                                 double fixed_nugget, double *ranges)
 {
 	const int nthetas = (kernel == EMUB_POWEREXP) ? d + 2 : 3;
 	double *scales = (double *)malloc(sizeof(double) * (size_t)d);
@@ -51,16 +52,27 @@ void emub_optimization_ranges(int kernel, const double *X, int ldx, int n, int d
 	ranges[0] = 0.0001; ranges[1] = range_max; /* amplitude (not optimised, kept for layout) */
 	ranges[2] = -5.0; ranges[3] = -2.0;        /* nugget, optstruct.c:153-154 */
 	for (int i = 2; i < nthetas; i++) {
-		if (kernel == EMUB_POWEREXP) {
-			range_min = 0.5 * log(scales[i - 2]);
-			range_max = log(25 * exp(range_min));
-		} else {
-			range_min = 0.5 * scales[i - 2];
+		if (use_data_scales) { /* :179-203; otherwise the defaults above, :205-211 */
+			if (kernel == EMUB_POWEREXP) {
+				range_min = 0.5 * log(scales[i - 2]);
+				range_max = log(25 * exp(range_min));
+			} else {
+				range_min = 0.5 * scales[i - 2];
+			}
 		}
 		ranges[2 * i] = range_min;
 		ranges[2 * i + 1] = range_max;
 	}
+	if (fixed_nugget_mode == 1) { /* :217-225: the lower end stays, the upper end is the fixed nugget + 20% */
+		ranges[2] = -5.0;
+		ranges[3] = fixed_nugget + 0.20 * fixed_nugget;
+	}
 	free(scales);
+}
+
+void emub_optimization_ranges(int kernel, const double *X, int ldx, int n, int d, double *ranges)
+{
+	emub_optimization_ranges_ex(kernel, X, ldx, n, d, 1, 0, 0.0, ranges);
 }
 
 static uint64_t splitmix64(uint64_t z)

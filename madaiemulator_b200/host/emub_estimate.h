@@ -62,6 +62,11 @@ void emub_estimate_default_opts(emub_estimate_opts *o);
  * no fixed nugget); ranges is nthetas x 2 row-major */
 void emub_sample_scales(const double *X, int ldx, int n, int d, double *scales);
 void emub_optimization_ranges(int kernel, const double *X, int ldx, int n, int d, double *ranges);
+/* the same with the two switches of the optstruct: use_data_scales = 0 keeps the default length ranges (optstruct.c:205-211),
+ * fixed_nugget_mode = 1 caps the nugget range at fixed_nugget + 20% (optstruct.c:217-225; callEstimate's use_fixed_nugget,
+ * rbind.c:43-60) */
+void emub_optimization_ranges_ex(int kernel, const double *X, int ldx, int n, int d, int use_data_scales, int fixed_nugget_mode,
+                                 double fixed_nugget, double *ranges);
 
 /* start point of restart `try_index`: uniform in ranges (set_random_init_value, maxmultimin.c:789-804) */
 void emub_random_init(unsigned long long seed, int try_index, const double *ranges, int nthetas, double *x);

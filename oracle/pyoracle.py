@@ -183,6 +183,9 @@ class RefOracle:
             L.ref_model_nregression_fns.argtypes = [_vp]
             L.ref_model_ranges.argtypes = [_vp, _dp]
             L.ref_model_sample_scales.argtypes = [_vp, _dp]
+            if hasattr(L, "ref_model_ranges_ex"):
+                L.ref_model_ranges_ex.argtypes = [_vp, _ci, _ci, ctypes.c_double, _dp]
+                L.ref_model_ranges_ex.restype = None
             L.ref_cov_matrix.argtypes = [_vp, _dp, _dp]
             L.ref_cov_pair.restype = ctypes.c_double
             L.ref_cov_pair.argtypes = [_vp, _dp, _dp, _dp]
@@ -251,6 +254,12 @@ class RefOracle:
     def ranges(self):
         r = np.empty((self.nthetas, 2))
         self.L.ref_model_ranges(self.h, _P(r))
+        return r
+
+    def ranges_ex(self, use_data_scales=True, fixed_nugget=None):
+        r = np.empty((self.nthetas, 2))
+        self.L.ref_model_ranges_ex(self.h, 1 if use_data_scales else 0, 0 if fixed_nugget is None else 1,
+                                   0.0 if fixed_nugget is None else float(fixed_nugget), _P(r))
         return r
 
     def eval(self, theta_less_amp):

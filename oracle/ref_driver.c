@@ -104,6 +104,27 @@ void ref_model_ranges(void *h, double *out)
 		out[2 * i + 1] = gsl_matrix_get(r->model->options->grad_ranges, i, 1);
 	}
 }
+/* -> setup_optimization_ranges, src/optstruct.c:142, with the optstruct's two switches set by the caller (what
+ * callEstimate's use_fixed_nugget does, src/libRbind/rbind.c:43-60): the model's options are modified for the call and
+ * restored */
+void ref_model_ranges_ex(void *h, int use_data_scales, int fixed_nugget_mode, double fixed_nugget, double *out)
+{
+	ref_model *r = (ref_model *)h;
+	optstruct *o = r->model->options;
+	const int s_uds = o->use_data_scales, s_fnm = o->fixed_nugget_mode;
+	const double s_fn = o->fixed_nugget;
+	gsl_matrix *s_ranges = o->grad_ranges;
+	o->use_data_scales = use_data_scales; o->fixed_nugget_mode = fixed_nugget_mode; o->fixed_nugget = fixed_nugget;
+	int saved = silence_stdout();
+	setup_optimization_ranges(o, r->model); /* allocates a fresh grad_ranges */
+	restore_stdout(saved);
+	for (int i = 0; i < o->nthetas; i++) {
+		out[2 * i] = gsl_matrix_get(o->grad_ranges, i, 0);
+		out[2 * i + 1] = gsl_matrix_get(o->grad_ranges, i, 1);
+	}
+	gsl_matrix_free(o->grad_ranges);
+	o->grad_ranges = s_ranges; o->use_data_scales = s_uds; o->fixed_nugget_mode = s_fnm; o->fixed_nugget = s_fn;
+}
 void ref_model_sample_scales(void *h, double *out)
 {
 	ref_model *r = (ref_model *)h;

@@ -59,7 +59,8 @@ def test_block_boundary_sizes(ctx, n):
 
 
 def test_largest_supported_dimensions(ctx):
-    """d = 32 (the staging limit), and d = 15 with cubic regression: p = 46 regression functions."""
+    """The staging limits: nparams up to 64 and up to 103 regression functions (cubic regression at d = 34, linear at
+    d = 64) -- well past the reference's own fixtures (d <= 15); beyond them the model is refused, not truncated."""
     X = ds.synthetic_design(200, 32)
     y = ds.synthetic_response(X[:, :15])
     th = np.concatenate([[-3.0], np.full(32, 1.2)])
@@ -68,11 +69,27 @@ def test_largest_supported_dimensions(ctx):
     y = ds.synthetic_response(X)
     th = np.concatenate([[-3.0], np.full(15, 1.0)])
     _check(ctx, X, y, 1, 3, th[None, :], np.concatenate([[0.1], th]), ds.synthetic_queries(6, 15))
+    # d = 16 with cubic regression (p = 49): refused before, SURVEY's reference has no such limit
+    X = ds.synthetic_design(300, 16, lo=-1.0, hi=1.0)
+    y = ds.synthetic_response(X[:, :15])
+    th = np.concatenate([[-3.0], np.full(16, 0.6)])
+    _check(ctx, X, y, 1, 3, th[None, :], np.concatenate([[0.1], th]), ds.synthetic_design(6, 16, seed=ds.SEED + 1, lo=-1.0, hi=1.0))
+    # d = 64 with linear regression (p = 65), d = 34 with cubic regression (p = 103)
+    X = ds.synthetic_design(330, 64)
+    y = ds.synthetic_response(X[:, :15])
+    th = np.concatenate([[-3.0], np.full(64, 1.6)])
+    _check(ctx, X, y, 1, 1, th[None, :], np.concatenate([[0.0], th]), ds.synthetic_queries(5, 64))
+    X = ds.synthetic_design(420, 34, lo=-1.0, hi=1.0)
+    y = ds.synthetic_response(X[:, :15])
+    th = np.concatenate([[-3.0], np.full(34, 0.9)])
+    q34 = ds.synthetic_design(5, 34, seed=ds.SEED + 1, lo=-1.0, hi=1.0)
+    _check(ctx, X, y, 1, 3, th[None, :], np.concatenate([[0.0], th]), q34)
+    _check(ctx, X, y, 3, 2, np.array([[-3.0, 1.2]]), np.array([1.3, 0.05, 1.2]), q34)
     from madaiemulator_b200 import engine
-    with pytest.raises(engine.EmubError):  # d = 33 is refused, not silently truncated
-        engine.Model(ctx, ds.synthetic_design(40, 33), np.zeros(40), 1, 0)
-    with pytest.raises(engine.EmubError):  # 1 + 3 * 16 + 1 = 50 columns > 48
-        engine.Model(ctx, ds.synthetic_design(80, 16), np.zeros(80), 1, 3)
+    with pytest.raises(engine.EmubError):  # d = 65 is refused, not silently truncated
+        engine.Model(ctx, ds.synthetic_design(40, 65), np.zeros(40), 1, 0)
+    with pytest.raises(engine.EmubError):  # 1 + 3 * 35 + 1 = 107 columns > 104
+        engine.Model(ctx, ds.synthetic_design(80, 35), np.zeros(80), 1, 3)
 
 
 def test_duplicated_design_points_get_the_nugget_off_diagonal(ctx):

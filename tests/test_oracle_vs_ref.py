@@ -66,3 +66,22 @@ def test_random_inits_follow_ranges():
     rg = r.ranges()
     x0 = r.random_inits(7, 50)
     assert np.all(x0 >= rg[:, 0]) and np.all(x0 <= rg[:, 1])
+
+
+def test_host_ranges_with_fixed_nugget_and_default_scales():
+    """emub_optimization_ranges_ex against the reference's setup_optimization_ranges (optstruct.c:142-226) with
+    fixed_nugget_mode = 1 (:217-225) and use_data_scales = 0 (:205-211), both kernels."""
+    from madaiemulator_b200 import datasets as ds
+    from madaiemulator_b200 import engine
+    from oracle.pyoracle import RefOracle, ref_available
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    X = ds.synthetic_design(60, 4)
+    y = ds.synthetic_response(X)
+    for kernel in (1, 2, 3):
+        ref = RefOracle(X, y, kernel, 0)
+        for uds in (True, False):
+            for fn in (None, 0.001, -3.5):
+                got = engine.optimization_ranges(kernel, X, use_data_scales=uds, fixed_nugget=fn)
+                assert np.array_equal(got, ref.ranges_ex(uds, fn)), (kernel, uds, fn)
+        assert np.array_equal(engine.optimization_ranges(kernel, X), ref.ranges())
