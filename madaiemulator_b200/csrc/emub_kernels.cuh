@@ -28,7 +28,9 @@ struct FewSet {
 //  [4 .. 4+d)       1 / (exp(theta_k))^2               emulator.c:123-127
 //  [4+d .. 4+2d)    0.5 * exp(-2 theta_k)              emulator.c:181,203
 //  [4+2d .. 4+3d)   exp(-2 theta_k)
-constexpr int CONST_STRIDE = 4 + 3 * MAXD;
+//  [4+3d .. 4+4d)   sqrt(0.5 / l_k^2 * 64/ln2)         covariance: coordinates are staged times this, so that the exponent
+//  [4+4d .. 4+5d)   sqrt(0.5 exp(-2 theta_k) * 64/ln2)  ... gradient                 is -sum_k (x'_ik - x'_jk)^2 in exp_scaled's units
+constexpr int CONST_STRIDE = 4 + 5 * MAXD;
 
 enum { THETA_LIK = 0 /* theta without amplitude, unit amplitude (maxmultimin.c:311-313; Matern: D-2) */,
        THETA_FULL = 1 /* literal full vector (emulator_struct.c:28) */ };
@@ -52,6 +54,8 @@ __global__ void k_theta_prep(const double *__restrict__ thetas, int B, int nth_i
 			double e2 = exp(-2.0 * len[k]);
 			c[4 + d + k] = 0.5 * e2;
 			c[4 + 2 * d + k] = e2;
+			c[4 + 3 * d + k] = sqrt((0.5 * c[4 + k]) * EXP_SCALE);
+			c[4 + 4 * d + k] = sqrt(c[4 + d + k] * EXP_SCALE);
 		}
 	} else {
 		if (mode == THETA_LIK) { c[0] = 1.0; c[1] = exp(th[0]); c[2] = exp(th[1]); }
@@ -79,24 +83,29 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 	double *sXi = sm;            // [d][64]
 	double *sXj = sm + d * CT;   // [d][64]
 	__shared__ double sc[CONST_STRIDE];
-	__shared__ double sh[MAXD];  // (-0.5 / l_k^2) * 64/ln2: the literal (-1/2 dist) dist / l^2 (scaling by 1/2 is exact; D-5) in exp_scaled's units
+	__shared__ double sh[MAXD];  // coincidence threshold per parameter, in staged units
 	__shared__ double stab[64 * EXP_REP];
 	exp_table_load<EXP_REP>(stab);
 	const int tid = threadIdx.x;
 	const double *cg = consts + b * const_stride;
 	for (int i = tid; i < 4 + 3 * d; i += 256) sc[i] = cg[i];
-	if (KERNEL == 1) for (int i = tid; i < d; i += 256) sh[i] = (-0.5 * cg[4 + i]) * EXP_SCALE;  // exponent in units of ln2/64 (exp_scaled)
+	// Power-exponential kernel: the coordinates are staged already multiplied by s_k = sqrt(0.5 / l_k^2 * 64/ln2), so the
+	// exponent (-1/2 dist) dist / l_k^2 (emulator.c:132, D-5) summed over k is -sum_k (x'_ik - x'_jk)^2 in exp_scaled's
+	// units: one subtraction and one fused multiply-add per pair and parameter.  sh[k] = 1e-10 * s_k is the
+	// coincidence threshold (emulator.c:136-150) in the same units.
+	if (KERNEL == 1) for (int i = tid; i < d; i += 256) sh[i] = 0.0000000001 * cg[4 + 3 * d + i];
 	const int i0 = bi * CT, j0 = bj * CT;
 	const int ncols = CROSS ? mq : n;
 	const double *XJ = CROSS ? Q : X;
 	for (int idx = tid; idx < CT * d; idx += 256) {
 		int r = idx / d, k = idx - r * d;
-		sXi[k * CT + r] = (i0 + r < n) ? X[(size_t)(i0 + r) * d + k] : 0.0;
-		sXj[k * CT + r] = (j0 + r < ncols) ? XJ[(size_t)(j0 + r) * d + k] : 0.0;
+		const double sk = (KERNEL == 1) ? cg[4 + 3 * d + k] : 1.0;
+		sXi[k * CT + r] = (i0 + r < n) ? X[(size_t)(i0 + r) * d + k] * sk : 0.0;
+		sXj[k * CT + r] = (j0 + r < ncols) ? XJ[(size_t)(j0 + r) * d + k] * sk : 0.0;
 	}
 	__syncthreads();
 	const int tx = tid & 15, ty = tid >> 4;
-	const double thr = (KERNEL == 1) ? 0.0000000001 : 0.0000000000000001;
+	const double thr0 = (KERNEL == 1) ? sh[0] : 0.0000000000000001;
 	double e[4][4];
 	unsigned same = 0;
 #pragma unroll
@@ -109,14 +118,13 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 		for (int r = 0; r < 4; r++) xi[r] = sXi[ty + 16 * r];
 #pragma unroll
 		for (int c = 0; c < 4; c++) xj[c] = sXj[tx + 16 * c];
-		const double h = (KERNEL == 1) ? sh[0] : 1.0;
 #pragma unroll
 		for (int r = 0; r < 4; r++)
 #pragma unroll
 			for (int c = 0; c < 4; c++) {
 				const double dist = fabs(xi[r] - xj[c]);
-				e[r][c] = (dist * dist) * h;
-				if (dist < thr) same |= 1u << (r * 4 + c);
+				e[r][c] = dist * dist;
+				if (dist < thr0) same |= 1u << (r * 4 + c);
 			}
 	}
 	for (int k = 1; k < d; k++) {
@@ -125,15 +133,15 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 		for (int r = 0; r < 4; r++) xi[r] = sXi[k * CT + ty + 16 * r];
 #pragma unroll
 		for (int c = 0; c < 4; c++) xj[c] = sXj[k * CT + tx + 16 * c];
-		const double h = (KERNEL == 1) ? sh[k] : 1.0;
 #pragma unroll
 		for (int r = 0; r < 4; r++)
 #pragma unroll
 			for (int c = 0; c < 4; c++) {
 				const double dl = xi[r] - xj[c];
-				e[r][c] = fma(dl * dl, h, e[r][c]);
+				e[r][c] = fma(dl, dl, e[r][c]);
 			}
 		if (same) {  // rare: only pairs that coincide in every parameter seen so far
+			const double thr = (KERNEL == 1) ? sh[k] : 0.0000000000000001;
 #pragma unroll
 			for (int r = 0; r < 4; r++)
 #pragma unroll
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(256) k_cov(const double *__restrict__ X, int n
 			double v;
 			if (gi < n && gj < ncols) {
 				if (KERNEL == 1) {
-					v = exp_scaled<EXP_REP>(e[r][c], stab) * sc[0];  // emulator.c:134
+					v = exp_scaled<EXP_REP>(-e[r][c], stab) * sc[0];  // emulator.c:134
 				} else {
 					// emulator.c:344-386 (Matern 3/2), :438-480 (Matern 5/2); e holds the squared distance
 					const double dist = sqrt(e[r][c]);
@@ -480,12 +488,15 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 	exp_table_load<EXP_REP>(stab);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const double *cg = consts + (size_t)b * CONST_STRIDE;
-	for (int i = tid; i < 4 + 3 * d; i += 256) sc[i] = cg[i];
+	for (int i = tid; i < 4 + 5 * d; i += 256) sc[i] = cg[i];
 	const int i0 = bi * CT, j0 = bj * CT;
+	// power-exponential: coordinates staged times s_k = sqrt(a_k 64/ln2), a_k = 0.5 exp(-2 theta_k), so that the exponent
+	// of the k-th factor, -a_k q_k, is z = -(x'_ik - x'_jk)^2 in exp_scaled's units and q_k = -z / s_k^2
 	for (int idx = tid; idx < CT * d; idx += 256) {
 		int r = idx / d, k = idx - r * d;
-		sXi[k * CT + r] = (i0 + r < n) ? X[(size_t)(i0 + r) * d + k] : 0.0;
-		sXj[k * CT + r] = (j0 + r < n) ? X[(size_t)(j0 + r) * d + k] : 0.0;
+		const double sk = (KERNEL == 1) ? cg[4 + 4 * d + k] : 1.0;
+		sXi[k * CT + r] = (i0 + r < n) ? X[(size_t)(i0 + r) * d + k] * sk : 0.0;
+		sXj[k * CT + r] = (j0 + r < n) ? X[(size_t)(j0 + r) * d + k] * sk : 0.0;
 	}
 	const double *AB = ABbase + b * strideAB;
 	if (tid < 2 * CT) {
@@ -521,21 +532,20 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 #pragma unroll
 			for (int c = 0; c < 4; c++) ex[r][c] = 0.0;
 		for (int k = 0; k < d; k++) {
-			const double ak = sc[4 + d + k];
 #pragma unroll
 			for (int r = 0; r < 4; r++) {
 				const double xi = sXi[k * CT + ty + 16 * r];
 #pragma unroll
 				for (int c = 0; c < 4; c++) {
 					const double dl = xi - sXj[k * CT + tx + 16 * c];
-					ex[r][c] += ak * (dl * dl);
+					ex[r][c] = fma(dl, dl, ex[r][c]);
 				}
 			}
 		}
 #pragma unroll
 		for (int r = 0; r < 4; r++)
 #pragma unroll
-			for (int c = 0; c < 4; c++) w[r][c] *= exp_neg<EXP_REP>(-ex[r][c], stab);
+			for (int c = 0; c < 4; c++) w[r][c] *= exp_scaled<EXP_REP>(-ex[r][c], stab);
 		for (int k = 0; k < d; k++) {
 			double s = 0.0;
 #pragma unroll
@@ -549,11 +559,10 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 			}
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-			if (lane == 0) red[warp][k] = s;
+			if (lane == 0) red[warp][k] = s / (sc[4 + 4 * d + k] * sc[4 + 4 * d + k]);  // q_k = (staged difference)^2 / s_k^2
 		}
 	} else if (KERNEL == 1) {
 		for (int k = 0; k < d; k++) {
-			const double akz = -sc[4 + d + k] * EXP_SCALE;  // -a_k in exp_scaled's units
 			double s = 0.0;
 #pragma unroll
 			for (int r = 0; r < 4; r++) {
@@ -561,13 +570,13 @@ __global__ void __launch_bounds__(256) k_grad_tiles(const double *__restrict__ C
 #pragma unroll
 				for (int c = 0; c < 4; c++) {
 					const double dl = xi - sXj[k * CT + tx + 16 * c];
-					const double q = dl * dl;
-					s += w[r][c] * (q * exp_scaled<EXP_REP>(akz * q, stab));
+					const double qs = dl * dl;  // q_k s_k^2 = a_k q_k in exp_scaled's units
+					s += w[r][c] * (qs * exp_scaled<EXP_REP>(-qs, stab));
 				}
 			}
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-			if (lane == 0) red[warp][k] = s;
+			if (lane == 0) red[warp][k] = s / (sc[4 + 4 * d + k] * sc[4 + 4 * d + k]);  // back to q_k exp(-a_k q_k)
 		}
 	} else {
 		const double root = (KERNEL == 2) ? 1.732050808 : 2.236067978;
@@ -633,7 +642,7 @@ __global__ void __launch_bounds__(256) k_grad_final(const double *__restrict__ p
 	const double amp = exact ? 1.0 : exp(log(sigma2));  // maxmultimin.c:514; the objective itself has unit amplitude
 	for (int k = 0; k < nslots; k++) {
 		double s = 0.0;
-		for (size_t tix = tid; tix < ntl; tix += 256) s += part[((size_t)b * ntl + tix) * MAXD + k];
+		for (size_t tix = tid; tix < ntl; tix += 256) s += part[((size_t)b * ntl + tix) * nslots + k];
 		s = block_sum_256(s, scratch);
 		if (tid == 0) {
 			const double e2 = (kernel == 1) ? cg[4 + 2 * d + k] : 1.0;

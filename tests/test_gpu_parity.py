@@ -319,7 +319,7 @@ def test_device_exp(ctx):
     assert np.all(rel < 2.5e-16 * (2.0 + np.abs(x[live])))
     small = live & (x > -1.0)
     assert (np.abs(got2[small] - ref[small]) / np.spacing(ref[small])).max() < 2.5
-    assert np.all(got2[x < -709.0] == 0.0)
+    assert np.all(np.abs(got2[x < -709.0]) < 1e-300)  # underflow: a subnormal with a zero high word, or 0
 
 
 def test_cfg3_matern52_batched_restarts(ctx):
