@@ -612,6 +612,7 @@ static void run_regression(emub_model *m, cudaStream_t st, int s0, int count, in
 	// b[mid:hi] -= L21 u[lo:mid].  b starts as Yh and lives in AB (free until the gradient stage).  The same launches
 	// serve the value-only and the gradient path, so both return the same bits.
 	const int *comp = m->dComp + s0;
+	const bool two_cols = m->p + 1 <= 2;  // regression order 0: y and the constant column
 	for (size_t lv = 0; lv < m->spine.size(); lv++) {
 		const SpineNode nd = m->spine[lv];
 		const int r_lo = nd.lo * TB, r_mid = nd.mid * TB, r_hi = nd.hi * TB;
@@ -620,13 +621,21 @@ static void run_regression(emub_model *m, cudaStream_t st, int s0, int count, in
 		const int *bcomp = lv == 0 ? comp : nullptr;
 		{
 			LaunchScope ls(c, EMUB_K_SKINNY, count * 4.0 * (double)(r_mid - r_lo) * (r_mid - r_lo) * nchunk_cols, st);
-			k_rows_times_range<true><<<dim3((r_mid - r_lo) / 32, nchunk_cols, count), 256, 0, st>>>(
-			    W, (long long)m->mat, m->npad, r_lo, r_lo, r_mid, bsrc, bstride, bcomp, nullptr, 0, nullptr, m->ncp, UG, sUG);
+			if (two_cols)
+				k_rows_times_range<true, 2><<<dim3((r_mid - r_lo) / 32, 1, count), 256, 0, st>>>(
+				    W, (long long)m->mat, m->npad, r_lo, r_lo, r_mid, bsrc, bstride, bcomp, nullptr, 0, nullptr, m->ncp, UG, sUG);
+			else
+				k_rows_times_range<true, 8><<<dim3((r_mid - r_lo) / 32, nchunk_cols, count), 256, 0, st>>>(
+				    W, (long long)m->mat, m->npad, r_lo, r_lo, r_mid, bsrc, bstride, bcomp, nullptr, 0, nullptr, m->ncp, UG, sUG);
 		}
 		if (r_hi > r_mid) {
 			LaunchScope ls(c, EMUB_K_SKINNY, count * 8.0 * (double)(r_hi - r_mid) * (r_mid - r_lo) * nchunk_cols, st);
-			k_rows_times_range<false><<<dim3((r_hi - r_mid) / 32, nchunk_cols, count), 256, 0, st>>>(
-			    L, (long long)m->mat, m->npad, r_mid, r_lo, r_mid, UG, sUG, nullptr, bsrc, bstride, bcomp, m->ncp, AB, sUG);
+			if (two_cols)
+				k_rows_times_range<false, 2><<<dim3((r_hi - r_mid) / 32, 1, count), 256, 0, st>>>(
+				    L, (long long)m->mat, m->npad, r_mid, r_lo, r_mid, UG, sUG, nullptr, bsrc, bstride, bcomp, m->ncp, AB, sUG);
+			else
+				k_rows_times_range<false, 8><<<dim3((r_hi - r_mid) / 32, nchunk_cols, count), 256, 0, st>>>(
+				    L, (long long)m->mat, m->npad, r_mid, r_lo, r_mid, UG, sUG, nullptr, bsrc, bstride, bcomp, m->ncp, AB, sUG);
 		}
 	}
 	{

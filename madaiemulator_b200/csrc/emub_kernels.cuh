@@ -215,7 +215,10 @@ __global__ void k_pad_identity(double *__restrict__ A, int npad, int n)
 // grid (nrows/32, ncp/8, B), 256 threads: one warp per 4 rows, lanes stride over the columns j.
 // V (and S) of slot b: base + comp[b] * stride when comp is given (the training vector / PCA component the slot
 // evaluates, shared by all slots), else base + b * stride (per-slot buffer).
-template <bool TRI>
+// NC = 8: eight columns per CTA column chunk (blockIdx.y); NC = 2: the first two columns only -- y and the constant
+// regression function, all there is for regression order 0 -- a quarter of the V traffic and of the multiply-adds
+// (V comes through L1/L2 at 64 bytes per lane and step with NC = 8, twice the bytes of the HBM stream of M).
+template <bool TRI, int NC>
 __global__ void __launch_bounds__(256) k_rows_times_range(const double *__restrict__ Mbase, long long strideM, int ld, int r_lo,
                                                           int j_lo, int j_hi, const double *__restrict__ Vbase, long long strideV,
                                                           const int *__restrict__ compV, const double *Sbase, long long strideS,
@@ -226,26 +229,34 @@ __global__ void __launch_bounds__(256) k_rows_times_range(const double *__restri
 	const int r0 = r_lo + blockIdx.x * 32 + warp * 4;
 	const double *M = Mbase + b * strideM;
 	const double *V = Vbase + (compV ? compV[b] : b) * strideV;
-	double acc[4][8];
+	double acc[4][NC];
 #pragma unroll
 	for (int r = 0; r < 4; r++)
 #pragma unroll
-		for (int c = 0; c < 8; c++) acc[r][c] = 0.0;
+		for (int c = 0; c < NC; c++) acc[r][c] = 0.0;
 	const int jmax = TRI ? min(r0 + 3, j_hi - 1) : j_hi - 1;
 	for (int j = j_lo + lane; j <= jmax; j += 32) {
-		const double4 v0 = *reinterpret_cast<const double4 *>(V + (size_t)j * ncp + c0);
-		const double4 v1 = *reinterpret_cast<const double4 *>(V + (size_t)j * ncp + c0 + 4);
+		double v[NC];
+		if (NC == 2) {
+			const double2 v0 = *reinterpret_cast<const double2 *>(V + (size_t)j * ncp + c0);
+			v[0] = v0.x; v[1] = v0.y;
+		} else {
+			const double4 v0 = *reinterpret_cast<const double4 *>(V + (size_t)j * ncp + c0);
+			const double4 v1 = *reinterpret_cast<const double4 *>(V + (size_t)j * ncp + c0 + 4);
+			v[0] = v0.x; v[1] = v0.y; v[2 % NC] = v0.z; v[3 % NC] = v0.w;
+			v[4 % NC] = v1.x; v[5 % NC] = v1.y; v[6 % NC] = v1.z; v[7 % NC] = v1.w;
+		}
 #pragma unroll
 		for (int r = 0; r < 4; r++) {
 			const double w = (!TRI || j <= r0 + r) ? M[(size_t)(r0 + r) * ld + j] : 0.0;
-			acc[r][0] += w * v0.x; acc[r][1] += w * v0.y; acc[r][2] += w * v0.z; acc[r][3] += w * v0.w;
-			acc[r][4] += w * v1.x; acc[r][5] += w * v1.y; acc[r][6] += w * v1.z; acc[r][7] += w * v1.w;
+#pragma unroll
+			for (int c = 0; c < NC; c++) acc[r][c] += w * v[c];
 		}
 	}
 #pragma unroll
 	for (int r = 0; r < 4; r++)
 #pragma unroll
-		for (int c = 0; c < 8; c++) {
+		for (int c = 0; c < NC; c++) {
 			double s = acc[r][c];
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -256,9 +267,14 @@ __global__ void __launch_bounds__(256) k_rows_times_range(const double *__restri
 		const double *S = Sbase ? Sbase + (compS ? compS[b] : b) * strideS + (size_t)(r0 + lane) * ncp + c0 : nullptr;
 #pragma unroll
 		for (int r = 0; r < 4; r++)
-			if (lane == r)
+			if (lane == r) {
 #pragma unroll
-				for (int c = 0; c < 8; c++) O[c] = S ? S[c] - acc[r][c] : acc[r][c];
+				for (int c = 0; c < NC; c++) O[c] = S ? S[c] - acc[r][c] : acc[r][c];
+				// the columns this instantiation skips are structural zeros of Yh
+				if (NC < 8 && !S)
+#pragma unroll
+					for (int c = NC; c < 8; c++) O[c] = 0.0;
+			}
 	}
 }
 
