@@ -653,10 +653,17 @@ static void run_regression(emub_model *m, cudaStream_t st, int s0, int count, in
 }
 
 // AB[:, first ncols8 chunks] = W^T UG
+// nchunk_cols = 0: column 0 only (alpha = W^T u)
 static void run_wt_times(emub_model *m, cudaStream_t st, int s0, int count, int nchunk_cols)
 {
 	const long long sUG = (long long)m->npad * m->ncp;
-	LaunchScope ls(m->ctx, EMUB_K_SKINNY, count * 4.0 * (double)m->mat * nchunk_cols, st);
+	LaunchScope ls(m->ctx, EMUB_K_SKINNY, count * 4.0 * (double)m->mat * (nchunk_cols ? nchunk_cols : 1), st);
+	if (nchunk_cols == 0) {
+		k_cols_times<true, 1><<<dim3(m->npad / 32, 1, count), 256, 0, st>>>(
+		    m->bufW + (size_t)s0 * m->mat, (long long)m->mat, m->npad, m->npad, m->dUG + (size_t)s0 * sUG, sUG, m->ncp,
+		    m->dAB + (size_t)s0 * sUG, sUG);
+		return;
+	}
 	k_cols_times<true><<<dim3(m->npad / 32, nchunk_cols, count), 256, 0, st>>>(
 	    m->bufW + (size_t)s0 * m->mat, (long long)m->mat, m->npad, m->npad, m->dUG + (size_t)s0 * sUG, sUG, m->ncp,
 	    m->dAB + (size_t)s0 * sUG, sUG);
@@ -717,7 +724,7 @@ static void run_group(emub_model *m, cudaStream_t st, int s0, int count, int nth
 	if (want_grad) {
 		run_lauum(m, st, s0, count);
 		// alpha = W^T u; the exact-gradient mode also reads C^-1 H = W^T G (every column chunk)
-		run_wt_times(m, st, s0, count, m->exact_grad ? (m->p + 1 + 7) / 8 : 1);
+		run_wt_times(m, st, s0, count, m->exact_grad ? (m->p + 1 + 7) / 8 : 0);
 		run_gradient(m, st, s0, count);
 	}
 }

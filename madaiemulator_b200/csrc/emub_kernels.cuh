@@ -281,38 +281,55 @@ __global__ void __launch_bounds__(256) k_rows_times_range(const double *__restri
 // (b) OUT[j][c0..c0+8) = sum_{i >= ibegin(j)} M[i][j] * V[i][c0..c0+8)
 // TRI: M = W lower triangular (i >= j); otherwise all nrows rows (M = K, n x mq).
 // grid (ncols/32, ncp/8, B), 256 threads: lanes = 32 consecutive columns, warps stride over rows.
-template <bool TRI>
+// NC = 8: the eight columns c0..c0+8 of V; NC = 1: column 0 only (alpha = W^T u, all the literal gradient reads of AB)
+template <bool TRI, int NC = 8>
 __global__ void __launch_bounds__(256) k_cols_times(const double *__restrict__ Mbase, long long strideM, int ld, int nrows,
                                                     const double *__restrict__ Vbase, long long strideV, int ncp,
                                                     double *__restrict__ Obase, long long strideO)
 {
-	__shared__ double red[8][32][9];
+	__shared__ double red[8][32][NC + 1];
 	const int b = blockIdx.z, c0 = blockIdx.y * 8;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int j0 = blockIdx.x * 32, j = j0 + lane;
 	const double *M = Mbase + b * strideM;
 	const double *V = Vbase + b * strideV;
-	double acc[8];
+	double acc[NC];
 #pragma unroll
-	for (int c = 0; c < 8; c++) acc[c] = 0.0;
+	for (int c = 0; c < NC; c++) acc[c] = 0.0;
 	const int ibeg = TRI ? j0 : 0;
+	if (NC == 1) {
+#pragma unroll 8
+		for (int i = ibeg + warp; i < nrows; i += 8) {
+			double m = M[(size_t)i * ld + j];
+			if (TRI && i < j) m = 0.0;
+			acc[0] += m * V[(size_t)i * ncp + c0];
+		}
+	} else {
 #pragma unroll 4
-	for (int i = ibeg + warp; i < nrows; i += 8) {
-		double m = M[(size_t)i * ld + j];
-		if (TRI && i < j) m = 0.0;
-		const double4 v0 = *reinterpret_cast<const double4 *>(V + (size_t)i * ncp + c0);
-		const double4 v1 = *reinterpret_cast<const double4 *>(V + (size_t)i * ncp + c0 + 4);
-		acc[0] += m * v0.x; acc[1] += m * v0.y; acc[2] += m * v0.z; acc[3] += m * v0.w;
-		acc[4] += m * v1.x; acc[5] += m * v1.y; acc[6] += m * v1.z; acc[7] += m * v1.w;
+		for (int i = ibeg + warp; i < nrows; i += 8) {
+			double m = M[(size_t)i * ld + j];
+			if (TRI && i < j) m = 0.0;
+			const double4 v0 = *reinterpret_cast<const double4 *>(V + (size_t)i * ncp + c0);
+			const double4 v1 = *reinterpret_cast<const double4 *>(V + (size_t)i * ncp + c0 + 4);
+			acc[0] += m * v0.x; acc[1 % NC] += m * v0.y; acc[2 % NC] += m * v0.z; acc[3 % NC] += m * v0.w;
+			acc[4 % NC] += m * v1.x; acc[5 % NC] += m * v1.y; acc[6 % NC] += m * v1.z; acc[7 % NC] += m * v1.w;
+		}
 	}
 #pragma unroll
-	for (int c = 0; c < 8; c++) red[warp][lane][c] = acc[c];
+	for (int c = 0; c < NC; c++) red[warp][lane][c] = acc[c];
 	__syncthreads();
-	{
+	if (NC == 1) {
+		if (threadIdx.x < 32) {
+			double s = 0.0;
+#pragma unroll
+			for (int w = 0; w < 8; w++) s += red[w][threadIdx.x][0];
+			Obase[b * strideO + (size_t)(j0 + threadIdx.x) * ncp + c0] = s;
+		}
+	} else {
 		const int l = threadIdx.x >> 3, c = threadIdx.x & 7;
 		double s = 0.0;
 #pragma unroll
-		for (int w = 0; w < 8; w++) s += red[w][l][c];
+		for (int w = 0; w < 8; w++) s += red[w][l][c % NC];
 		Obase[b * strideO + (size_t)(j0 + l) * ncp + c0 + c] = s;
 	}
 }
