@@ -104,6 +104,12 @@ int emub_loglik_grad_batch(emub_model *m, const double *thetas, int B, int want_
  * fronts of all components of a multivariate model (estimate_multi, multivar_support.c:20-27) share one batch */
 int emub_loglik_grad_batch_comp(emub_model *m, const double *thetas, const int *comp, int B, int want_grad,
                                 double *negL, double *grad, double *sigma2, int *status);
+/* same with a gradient request per point: want_grad[b] != 0 evaluates the gradient of point b (evalFnGradMulti), 0 the
+ * value alone (evalFnMulti: the factor without the inverse, about 0.38 of the work).  The two kinds share every launch
+ * they have in common, so a front that mixes line-search trial points with accepted ones stays one batched call;
+ * grad rows of value-only points are zero.  Values are bit-identical to the uniform calls. */
+int emub_loglik_grad_batch_mixed(emub_model *m, const double *thetas, const int *comp, const int *want_grad, int B,
+                                 double *negL, double *grad, double *sigma2, int *status);
 /* same, but thetas / outputs are DEVICE pointers (out: B x (nthetas+3) doubles per point:
  * negL, sigma2, status, logdet, grad[nthetas-1]); asynchronous on the context's streams until
  * emub_ctx_synchronize. */

@@ -559,14 +559,16 @@ static void launch_kcross(emub_model *m, cudaStream_t st, const double *consts, 
 
 // L (bufT) and W = L^-1 (bufW) from C (bufA) for `count` slots starting at s0
 // full = false: the factor only (the merges of the right spine of the recursion are skipped, see build_factor)
-static void run_factor(emub_model *m, cudaStream_t st, int s0, int count, bool full)
+// The first nfull of the slots also get the merges of the right spine (the whole W = L^-1); the others the factor only.
+static void run_factor(emub_model *m, cudaStream_t st, int s0, int nslots, int nfull)
 {
 	emub_ctx *c = m->ctx;
 	const int ld = m->npad;
 	const long long ms = (long long)m->mat;
 	double *A = m->bufA + (size_t)s0 * m->mat, *W = m->bufW + (size_t)s0 * m->mat, *T = m->bufT + (size_t)s0 * m->mat;
 	for (const FactorStep &s : m->steps) {
-		if (s.full_only && !full) continue;
+		const int count = s.full_only ? nfull : nslots;
+		if (count <= 0) continue;
 		const GemmTask *tk = m->dTasks + s.off;
 		switch (s.type) {
 		case STEP_POTF2: {
@@ -707,8 +709,9 @@ static void run_gradient(emub_model *m, cudaStream_t st, int s0, int count)
 	}
 }
 
-// factorise + likelihood (+ gradient) for slots [s0, s0+count) whose thetas are already in dThetas
-static void run_group(emub_model *m, cudaStream_t st, int s0, int count, int nth_in, int mode, int want_grad, int emulator_mode)
+// factorise + likelihood for slots [s0, s0+count) whose thetas are already in dThetas; the first ngrad of them also get
+// the gradient (whole inverse, C^-1 = W^T W, fused reduction)
+static void run_group(emub_model *m, cudaStream_t st, int s0, int count, int nth_in, int mode, int ngrad, int emulator_mode)
 {
 	emub_ctx *c = m->ctx;
 	{
@@ -719,27 +722,31 @@ static void run_group(emub_model *m, cudaStream_t st, int s0, int count, int nth
 	cudaMemsetAsync(m->dInfo + s0, 0, sizeof(int) * count, st);
 	launch_cov(m, st, count, m->dConsts + (size_t)s0 * CONST_STRIDE, m->bufA + (size_t)s0 * m->mat, (long long)m->mat, 1);
 	// the whole triangular inverse is only needed for C^-1 (gradient) and for prediction (W K)
-	run_factor(m, st, s0, count, want_grad || emulator_mode);
+	run_factor(m, st, s0, count, emulator_mode ? count : ngrad);
 	run_regression(m, st, s0, count, emulator_mode);
-	if (want_grad) {
-		run_lauum(m, st, s0, count);
+	if (ngrad > 0) {
+		run_lauum(m, st, s0, ngrad);
 		// alpha = W^T u; the exact-gradient mode also reads C^-1 H = W^T G (every column chunk)
-		run_wt_times(m, st, s0, count, m->exact_grad ? (m->p + 1 + 7) / 8 : 0);
-		run_gradient(m, st, s0, count);
+		run_wt_times(m, st, s0, ngrad, m->exact_grad ? (m->p + 1 + 7) / 8 : 0);
+		run_gradient(m, st, s0, ngrad);
 	}
 }
 
+// how the slots of a chunk are shared out: group g owns cnt(g) consecutive slots, the first ngl(g) of which evaluate
+// the gradient (the host front orders the points of a chunk accordingly, chunk_slot_order)
+static inline int group_count(int total, int ng, int g) { return total / ng + (g < total % ng ? 1 : 0); }
+
 // split `count` slots over the context's stream groups and run them concurrently
 // the launch sequence of one chunk: fork stream 0 to the other groups, run them, join back
-static int issue_chunk(emub_model *m, int count, int nth_in, int mode, int want_grad, int emulator_mode, int ng)
+static int issue_chunk(emub_model *m, int count, int nth_in, int mode, int ngrad, int emulator_mode, int ng)
 {
 	emub_ctx *c = m->ctx;
 	CUDA_TRY(cudaEventRecord(c->gev[0], c->streams[0]));
 	int s0 = 0;
 	for (int g = 0; g < ng; g++) {
-		int cnt = count / ng + (g < count % ng ? 1 : 0);
+		const int cnt = group_count(count, ng, g);
 		if (g > 0) CUDA_TRY(cudaStreamWaitEvent(c->streams[g], c->gev[0], 0));
-		run_group(m, c->streams[g], s0, cnt, nth_in, mode, want_grad, emulator_mode);
+		run_group(m, c->streams[g], s0, cnt, nth_in, mode, group_count(ngrad, ng, g), emulator_mode);
 		s0 += cnt;
 		if (g > 0) {
 			CUDA_TRY(cudaEventRecord(c->gev[g], c->streams[g]));
@@ -753,28 +760,48 @@ static int issue_chunk(emub_model *m, int count, int nth_in, int mode, int want_
 // sizes) depend only on (count, theta layout, gradient / emulator flags, groups): it is captured ONCE into a CUDA
 // graph (the fork/join events between the group streams become graph edges) and replayed afterwards, so the
 // host pays one launch per chunk and the small dependent kernels of the recursion run back to back.
-static int run_chunk(emub_model *m, int count, int nth_in, int mode, int want_grad, int emulator_mode)
+static int chunk_groups(const emub_model *m, int count) { return m->ctx->profile ? 1 : std::min(m->ctx->ngroups, count); }
+
+// ngrad: how many of the count points evaluate the gradient (they sit first in every group's slot range)
+static int run_chunk(emub_model *m, int count, int nth_in, int mode, int ngrad, int emulator_mode)
 {
 	emub_ctx *c = m->ctx;
-	const int ng = c->profile ? 1 : std::min(c->ngroups, count);
+	const int ng = chunk_groups(m, count);
 	m->last_count = count;
 	if (c->profile || !c->use_graphs) {
-		int rc = issue_chunk(m, count, nth_in, mode, want_grad, emulator_mode, ng);
+		int rc = issue_chunk(m, count, nth_in, mode, ngrad, emulator_mode, ng);
 		if (rc) return rc;
 		CUDA_TRY(cudaGetLastError());
 		return EMUB_OK;
 	}
-	const unsigned long long key = ((unsigned long long)count << 32) | ((unsigned)nth_in << 16) | ((unsigned)ng << 8) |
-	                               ((unsigned)(m->exact_grad != 0) << 4) | ((unsigned)mode << 2) | ((unsigned)(want_grad != 0) << 1) |
+	const unsigned long long key = ((unsigned long long)count << 48) | ((unsigned long long)ngrad << 32) | ((unsigned)nth_in << 16) |
+	                               ((unsigned)ng << 8) | ((unsigned)(m->exact_grad != 0) << 4) | ((unsigned)mode << 2) |
 	                               (unsigned)(emulator_mode != 0);
 	cudaGraphExec_t exec = nullptr;
-	for (auto &g : m->graphs)
-		if (g.first == key) { exec = g.second; break; }
+	long long nlaunch = 0;
+	for (size_t i = 0; i < m->graphs.size(); i++)
+		if (m->graphs[i].first == key) {
+			exec = m->graphs[i].second;
+			nlaunch = m->graph_launches[i].second;
+			if (i + 1 < m->graphs.size()) {  // most recently used last
+				std::rotate(m->graphs.begin() + i, m->graphs.begin() + i + 1, m->graphs.end());
+				std::rotate(m->graph_launches.begin() + i, m->graph_launches.begin() + i + 1, m->graph_launches.end());
+			}
+			break;
+		}
 	if (!exec) {
+		// a front of restart chains produces many (count, ngrad) shapes: keep the most recently used ones
+		constexpr size_t GRAPH_CACHE = 96;
+		if (m->graphs.size() >= GRAPH_CACHE) {
+			CUDA_TRY(cudaStreamSynchronize(c->streams[0]));
+			cudaGraphExecDestroy(m->graphs.front().second);
+			m->graphs.erase(m->graphs.begin());
+			m->graph_launches.erase(m->graph_launches.begin());
+		}
 		const long long launches_before = c->launches;
 		cudaGraph_t graph = nullptr;
 		CUDA_TRY(cudaStreamBeginCapture(c->streams[0], cudaStreamCaptureModeThreadLocal));
-		int rc = issue_chunk(m, count, nth_in, mode, want_grad, emulator_mode, ng);
+		int rc = issue_chunk(m, count, nth_in, mode, ngrad, emulator_mode, ng);
 		cudaError_t ce = cudaStreamEndCapture(c->streams[0], &graph);
 		if (rc != EMUB_OK || ce != cudaSuccess || !graph) {
 			if (graph) cudaGraphDestroy(graph);
@@ -784,12 +811,12 @@ static int run_chunk(emub_model *m, int count, int nth_in, int mode, int want_gr
 		ce = cudaGraphInstantiate(&exec, graph, 0);
 		cudaGraphDestroy(graph);
 		if (ce != cudaSuccess) return set_err(EMUB_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+		nlaunch = c->launches - launches_before;
 		m->graphs.push_back({key, exec});
-		m->graph_launches.push_back({key, c->launches - launches_before});
+		m->graph_launches.push_back({key, nlaunch});
 		c->launches = launches_before;  // counted per replay below
 	}
-	for (auto &g : m->graph_launches)
-		if (g.first == key) { c->launches += g.second; break; }
+	c->launches += nlaunch;
 	CUDA_TRY(cudaGraphLaunch(exec, c->streams[0]));
 	return EMUB_OK;
 }
@@ -818,7 +845,7 @@ extern "C" int emub_loglik_grad_batch_dev(emub_model *m, const double *d_thetas,
 		int rc = upload_components(m, nullptr, done, count, st);
 		if (rc) return rc;
 		CUDA_TRY(cudaMemcpyAsync(m->dThetas, d_thetas + (size_t)done * nth1, sizeof(double) * count * nth1, cudaMemcpyDeviceToDevice, st));
-		rc = run_chunk(m, count, nth1, THETA_LIK, want_grad, 0);
+		rc = run_chunk(m, count, nth1, THETA_LIK, want_grad ? count : 0, 0);
 		if (rc) return rc;
 		{
 			LaunchScope ls(c, EMUB_K_SMALL, 0, st);
@@ -829,35 +856,82 @@ extern "C" int emub_loglik_grad_batch_dev(emub_model *m, const double *d_thetas,
 	return EMUB_OK;
 }
 
-extern "C" int emub_loglik_grad_batch_comp(emub_model *m, const double *thetas, const int *comp, int B, int want_grad,
-                                           double *negL, double *grad, double *sigma2, int *status)
+// The host-pointer evaluation: want[b] != 0 asks for the gradient of point b (want == NULL: want_all for every point).
+// Within a chunk the gradient points are placed first in every stream group's slot range, so that the launches of the
+// gradient-only stages (spine merges of the inverse, W^T W, the fused reduction) cover a contiguous run of slots; the
+// results go back to the caller's order.  Values do not depend on where a point sits.
+static int loglik_batch_host(emub_model *m, const double *thetas, const int *comp, const int *want, int want_all, int B,
+                             double *negL, double *grad, double *sigma2, int *status)
 {
 	if (!m || !thetas || B < 0) return set_err(EMUB_EINVAL, "emub_loglik_grad_batch: bad argument%s");
 	emub_ctx *c = m->ctx;
 	CUDA_TRY(cudaSetDevice(c->device));
 	const int nth1 = m->nth - 1;
 	cudaStream_t st = c->streams[0];
+	std::vector<int> perm((size_t)std::max(1, std::min(B, m->nslots)));
 	for (int done = 0; done < B; done += m->nslots) {
 		const int count = std::min(m->nslots, B - done);
-		int rc = upload_components(m, comp, done, count, st);
-		if (rc) return rc;
-		memcpy(m->hThetas, thetas + (size_t)done * nth1, sizeof(double) * count * nth1);
+		const int ng = chunk_groups(m, count);
+		int ngrad = 0;
+		for (int b = 0; b < count; b++) ngrad += (want ? want[done + b] != 0 : want_all != 0);
+		// slot -> point: group g takes its share of the gradient points, then its share of the others
+		{
+			int ig = 0, iv = 0, slot = 0;
+			auto next = [&](bool g) {
+				int &i = g ? ig : iv;
+				while ((want ? want[done + i] != 0 : want_all != 0) != g) i++;
+				return i++;
+			};
+			for (int g = 0; g < ng; g++) {
+				const int cnt = group_count(count, ng, g), ngl = group_count(ngrad, ng, g);
+				for (int k = 0; k < cnt; k++) perm[slot++] = next(k < ngl);
+			}
+		}
+		for (int s = 0; s < count; s++) {
+			const int b = done + perm[s];
+			const int cidx = comp ? comp[b] : 0;
+			if (cidx < 0 || cidx >= m->ncomp) return set_err(EMUB_EINVAL, "emub: component index out of range%s");
+			m->hComp[s] = cidx;
+			memcpy(m->hThetas + (size_t)s * nth1, thetas + (size_t)b * nth1, sizeof(double) * nth1);
+		}
+		CUDA_TRY(cudaMemcpyAsync(m->dComp, m->hComp, sizeof(int) * count, cudaMemcpyHostToDevice, st));
 		CUDA_TRY(cudaMemcpyAsync(m->dThetas, m->hThetas, sizeof(double) * count * nth1, cudaMemcpyHostToDevice, st));
-		rc = run_chunk(m, count, nth1, THETA_LIK, want_grad, 0);
+		int rc = run_chunk(m, count, nth1, THETA_LIK, ngrad, 0);
 		if (rc) return rc;
 		CUDA_TRY(cudaMemcpyAsync(m->hRes, m->dRes, sizeof(double) * count * RES_STRIDE, cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
-		for (int b = 0; b < count; b++) {
-			const double *r = m->hRes + (size_t)b * RES_STRIDE;
+		for (int s = 0; s < count; s++) {
+			const int b = done + perm[s];
+			const double *r = m->hRes + (size_t)s * RES_STRIDE;
 			const int stt = (int)r[2];
-			if (negL) negL[done + b] = r[0];
-			if (sigma2) sigma2[done + b] = r[1];
-			if (status) status[done + b] = stt;
+			const bool wg = want ? want[b] != 0 : want_all != 0;
+			if (negL) negL[b] = r[0];
+			if (sigma2) sigma2[b] = r[1];
+			if (status) status[b] = stt;
 			if (grad)
-				for (int k = 0; k < nth1; k++) grad[(size_t)(done + b) * nth1 + k] = (want_grad || stt) ? r[RES_GRAD + k] : 0.0;
+				for (int k = 0; k < nth1; k++) grad[(size_t)b * nth1 + k] = wg ? r[RES_GRAD + k] : (stt ? nan("") : 0.0);
+		}
+		// emub_loglik_extras addresses the last chunk by point index: undo the slot order in place
+		if (count > 1) {
+			std::vector<double> tmp((size_t)count * RES_STRIDE);
+			for (int s = 0; s < count; s++) memcpy(&tmp[(size_t)perm[s] * RES_STRIDE], m->hRes + (size_t)s * RES_STRIDE, sizeof(double) * RES_STRIDE);
+			memcpy(m->hRes, tmp.data(), sizeof(double) * tmp.size());
 		}
 	}
 	return EMUB_OK;
+}
+
+extern "C" int emub_loglik_grad_batch_comp(emub_model *m, const double *thetas, const int *comp, int B, int want_grad,
+                                           double *negL, double *grad, double *sigma2, int *status)
+{
+	return loglik_batch_host(m, thetas, comp, nullptr, want_grad, B, negL, grad, sigma2, status);
+}
+
+extern "C" int emub_loglik_grad_batch_mixed(emub_model *m, const double *thetas, const int *comp, const int *want_grad, int B,
+                                            double *negL, double *grad, double *sigma2, int *status)
+{
+	if (!want_grad) return set_err(EMUB_EINVAL, "emub_loglik_grad_batch_mixed: null want_grad%s");
+	return loglik_batch_host(m, thetas, comp, want_grad, 0, B, negL, grad, sigma2, status);
 }
 
 extern "C" int emub_loglik_grad_batch(emub_model *m, const double *thetas, int B, int want_grad, double *negL, double *grad,
@@ -943,7 +1017,7 @@ extern "C" int emub_spd_inverse(emub_model *m, const double *A, int lda, double 
 		k_pad_identity<<<(npad - n + 127) / 128, 128, 0, st>>>(m->bufA, npad, n);
 	}
 	CUDA_TRY(cudaMemsetAsync(m->dInfo, 0, sizeof(int), st));
-	run_factor(m, st, 0, 1, true);
+	run_factor(m, st, 0, 1, 1);
 	run_lauum(m, st, 0, 1);
 	CUDA_TRY(cudaMemcpy2DAsync(Ainv, sizeof(double) * ldi, m->bufA, sizeof(double) * npad, sizeof(double) * n, n, cudaMemcpyDeviceToHost, st));
 	std::vector<double> parts(m->nblk);
@@ -1021,7 +1095,7 @@ extern "C" int emub_debug_cholesky(emub_model *m, const double *theta_less_amp, 
 	}
 	CUDA_TRY(cudaMemsetAsync(m->dInfo, 0, sizeof(int), st));
 	launch_cov(m, st, 1, m->dConsts, m->bufA, (long long)m->mat, 1);
-	run_factor(m, st, 0, 1, true);
+	run_factor(m, st, 0, 1, 1);
 	CUDA_TRY(cudaStreamSynchronize(st));
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemcpy2D(L, sizeof(double) * ldl, m->bufT, sizeof(double) * m->npad, sizeof(double) * m->n, m->n, cudaMemcpyDeviceToHost));

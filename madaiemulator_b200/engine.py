@@ -32,7 +32,7 @@ SYMBOLS = [
     "emub_ctx_create", "emub_ctx_destroy", "emub_last_error", "emub_version", "emub_ctx_stream",
     "emub_ctx_set_groups", "emub_ctx_use_graphs", "emub_model_create", "emub_model_destroy", "emub_model_nthetas",
     "emub_model_nregression_fns", "emub_model_slots", "emub_model_kernel", "emub_spd_inverse", "emub_model_set_training", "emub_model_set_training_multi",
-    "emub_model_ncomponents", "emub_model_set_gradient_mode", "emub_model_gradient_mode", "emub_loglik_grad_batch_comp", "emub_emulator_create_comp", "emub_predict_multi", "emub_predict_multi_few", "emub_cov_matrix",
+    "emub_model_ncomponents", "emub_model_set_gradient_mode", "emub_model_gradient_mode", "emub_loglik_grad_batch_comp", "emub_loglik_grad_batch_mixed", "emub_emulator_create_comp", "emub_predict_multi", "emub_predict_multi_few", "emub_cov_matrix",
     "emub_h_matrix", "emub_k_vectors", "emub_loglik_grad_batch", "emub_loglik_grad_batch_dev",
     "emub_ctx_synchronize", "emub_loglik_extras", "emub_emulator_create", "emub_emulator_destroy",
     "emub_emulator_beta", "emub_predict_batch", "emub_predict_few", "emub_predict_batch_dev", "emub_profile_enable",
@@ -85,6 +85,7 @@ def lib():
     L.emub_model_set_training_multi.argtypes = [_vp, _dp, _ci, _ci]
     L.emub_model_ncomponents.argtypes = [_vp]
     L.emub_loglik_grad_batch_comp.argtypes = [_vp, _dp, _ip, _ci, _ci, _dp, _dp, _dp, _ip]
+    L.emub_loglik_grad_batch_mixed.argtypes = [_vp, _dp, _ip, _ip, _ci, _dp, _dp, _dp, _ip]
     L.emub_emulator_create_comp.argtypes = [_vp, _ci, _dp, ctypes.POINTER(_vp)]
     L.emub_predict_multi.argtypes = [ctypes.POINTER(_vp), _ci, _dp, _ci, _ci, _ci, _dp, _dp, _dp, _dp, _dp]
     L.emub_predict_multi_few.argtypes = [ctypes.POINTER(_vp), _ci, _dp, _ci, _ci, _ci, _dp, _dp, _dp, _dp, _dp]
@@ -251,6 +252,12 @@ class Model:
         if comp is not None:
             comp = np.ascontiguousarray(comp, dtype=np.int32)
             cp = comp.ctypes.data_as(_ip)
+        if isinstance(want_grad, (list, tuple, np.ndarray)):  # a gradient request per point (emub_loglik_grad_batch_mixed)
+            wg = np.ascontiguousarray(want_grad, dtype=np.int32)
+            assert wg.shape == (B,)
+            _check(self.L.emub_loglik_grad_batch_mixed(self.h, _P(th), cp, wg.ctypes.data_as(_ip), B, _P(negL), _P(grad), _P(s2),
+                                                       st.ctypes.data_as(_ip)))
+            return dict(negL=negL, grad=grad, sigma2=s2, status=st)
         _check(self.L.emub_loglik_grad_batch_comp(self.h, _P(th), cp, B, 1 if want_grad else 0, _P(negL), _P(grad), _P(s2),
                                                   st.ctypes.data_as(_ip)))
         return dict(negL=negL, grad=grad, sigma2=s2, status=st)

@@ -400,30 +400,25 @@ static int estimate_front(emub_model *model, int ncomp, const double *ranges, co
 	int *bst = (int *)malloc(sizeof(int) * (size_t)nchains);
 	int *who = (int *)malloc(sizeof(int) * (size_t)nchains);
 	int *bcomp = (int *)malloc(sizeof(int) * (size_t)nchains);
+	int *bwant = (int *)malloc(sizeof(int) * (size_t)nchains);
 	int rc = EMUB_OK;
 	pthread_mutex_lock(&fr.mu);
 	for (;;) {
 		while (fr.nactive > 0 && fr.npending < fr.nactive) pthread_cond_wait(&fr.cv_disp, &fr.mu);
 		if (fr.nactive == 0) break;
-		/* the front in two batched calls: the points that need the gradient, then the value-only ones */
-		int B = 0, Bg = 0;
-		for (int pass = 1; pass >= 0; pass--) {
-			for (int i = 0; i < nchains; i++)
-				if (fr.chains[i].state == REQ_PENDING && fr.chains[i].want_grad == pass) {
-					memcpy(bx + (size_t)B * fr.nth1, fr.chains[i].x, sizeof(double) * (size_t)fr.nth1);
-					bcomp[B] = fr.chains[i].comp;
-					who[B++] = i;
-				}
-			if (pass == 1) Bg = B;
-		}
+		/* the whole front in ONE batched call; every point says whether it needs the gradient (the value-only points
+		 * skip the inverse, emub_loglik_grad_batch_mixed) */
+		int B = 0;
+		for (int i = 0; i < nchains; i++)
+			if (fr.chains[i].state == REQ_PENDING) {
+				memcpy(bx + (size_t)B * fr.nth1, fr.chains[i].x, sizeof(double) * (size_t)fr.nth1);
+				bcomp[B] = fr.chains[i].comp;
+				bwant[B] = fr.chains[i].want_grad;
+				who[B++] = i;
+			}
 		pthread_mutex_unlock(&fr.mu);
-		int call = EMUB_OK;
-		if (Bg > 0) { call = emub_loglik_grad_batch_comp(model, bx, bcomp, Bg, 1, bf, bg, bs, bst); fr.batches++; }
-		if (call == EMUB_OK && B > Bg) {
-			call = emub_loglik_grad_batch_comp(model, bx + (size_t)Bg * fr.nth1, bcomp + Bg, B - Bg, 0, bf + Bg, bg + (size_t)Bg * fr.nth1,
-			                                   bs + Bg, bst + Bg);
-			fr.batches++;
-		}
+		int call = emub_loglik_grad_batch_mixed(model, bx, bcomp, bwant, B, bf, bg, bs, bst);
+		fr.batches++;
 		pthread_mutex_lock(&fr.mu);
 		if (call != EMUB_OK) { rc = call; fr.failed = 1; }
 		fr.evaluations += B;
@@ -477,7 +472,7 @@ static int estimate_front(emub_model *model, int ncomp, const double *ranges, co
 		chain_t *c = &fr.chains[i];
 		free(c->x); free(c->g); free(c->cx); free(c->cg); free(c->best_thetas);
 	}
-	free(fr.chains); free(tids); free(bx); free(bg); free(bf); free(bs); free(bst); free(who); free(bcomp);
+	free(fr.chains); free(tids); free(bx); free(bg); free(bf); free(bs); free(bst); free(who); free(bcomp); free(bwant);
 	pthread_mutex_destroy(&fr.mu); pthread_cond_destroy(&fr.cv_disp); pthread_cond_destroy(&fr.cv_done);
 	if (rc != EMUB_OK) return rc;
 	return nfailed_comp ? EMUB_EDOM : EMUB_OK;

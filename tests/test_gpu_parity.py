@@ -196,6 +196,39 @@ def test_value_only_path_skips_the_inverse_and_returns_the_same_bits(ctx):
         m.close()
 
 
+def test_mixed_gradient_requests_in_one_batch(ctx):
+    """emub_loglik_grad_batch_mixed: a gradient flag per point; gradient and value-only points share one batched call
+    (what the restart front sends: accepted points next to line-search trial points).  Same bits as the uniform calls,
+    whatever the pattern, the batch size against the slot count, or the number of stream groups."""
+    from madaiemulator_b200 import engine
+    n, d = 390, 4
+    X = ds.synthetic_design(n, d)
+    Y = np.stack([ds.synthetic_response(X, t) for t in range(3)], axis=1)
+    m = engine.Model(ctx, X, Y[:, 0], 1, 1, max_slots=5)
+    m.set_training_multi(Y)
+    rng = np.random.default_rng(8)
+    B = 13
+    ths = np.stack([np.concatenate([[rng.uniform(-5, -2)], rng.uniform(0.0, 1.5, d)]) for _ in range(B)])
+    ths[4] = np.concatenate([[-800.0], np.full(d, 20.0)])  # not positive definite
+    comp = rng.integers(0, 3, B)
+    full = m.loglik_grad_batch(ths, want_grad=True, comp=comp)
+    for groups in (1, 2, 3):
+        ctx.set_groups(groups)
+        for pattern in (rng.integers(0, 2, B), np.zeros(B, int), np.ones(B, int), np.eye(B, dtype=int)[7]):
+            r = m.loglik_grad_batch(ths, want_grad=np.asarray(pattern), comp=comp)
+            assert np.array_equal(r["negL"], full["negL"], equal_nan=True) and np.array_equal(r["sigma2"], full["sigma2"], equal_nan=True)
+            assert np.array_equal(r["status"], full["status"]) and r["status"][4] == engine.EDOM
+            for b in range(B):
+                if pattern[b]:
+                    assert np.array_equal(r["grad"][b], full["grad"][b], equal_nan=True)
+                elif b != 4:
+                    assert np.all(r["grad"][b] == 0.0)
+                else:
+                    assert np.all(np.isnan(r["grad"][b]))
+    ctx.set_groups(2)
+    m.close()
+
+
 def test_spd_inverse_of_a_caller_matrix(ctx):
     """chol_inverse_cov_matrix (emulate-fns.c:275-300) on the engine: inverse and determinant of a host matrix."""
     from madaiemulator_b200 import engine
