@@ -624,19 +624,19 @@ static void run_regression(emub_model *m, cudaStream_t st, int s0, int count, in
 		{
 			LaunchScope ls(c, EMUB_K_SKINNY, count * 4.0 * (double)(r_mid - r_lo) * (r_mid - r_lo) * nchunk_cols, st);
 			if (two_cols)
-				k_rows_times_range<true, 2><<<dim3((r_mid - r_lo) / 32, 1, count), 256, 0, st>>>(
+				k_rows_times_range<true, 2><<<dim3((r_mid - r_lo) / 4, 1, count), 256, 0, st>>>(
 				    W, (long long)m->mat, m->npad, r_lo, r_lo, r_mid, bsrc, bstride, bcomp, nullptr, 0, nullptr, m->ncp, UG, sUG);
 			else
-				k_rows_times_range<true, 8><<<dim3((r_mid - r_lo) / 32, nchunk_cols, count), 256, 0, st>>>(
+				k_rows_times_range<true, 8><<<dim3((r_mid - r_lo) / 4, nchunk_cols, count), 256, 0, st>>>(
 				    W, (long long)m->mat, m->npad, r_lo, r_lo, r_mid, bsrc, bstride, bcomp, nullptr, 0, nullptr, m->ncp, UG, sUG);
 		}
 		if (r_hi > r_mid) {
 			LaunchScope ls(c, EMUB_K_SKINNY, count * 8.0 * (double)(r_hi - r_mid) * (r_mid - r_lo) * nchunk_cols, st);
 			if (two_cols)
-				k_rows_times_range<false, 2><<<dim3((r_hi - r_mid) / 32, 1, count), 256, 0, st>>>(
+				k_rows_times_range<false, 2><<<dim3((r_hi - r_mid) / 4, 1, count), 256, 0, st>>>(
 				    L, (long long)m->mat, m->npad, r_mid, r_lo, r_mid, UG, sUG, nullptr, bsrc, bstride, bcomp, m->ncp, AB, sUG);
 			else
-				k_rows_times_range<false, 8><<<dim3((r_hi - r_mid) / 32, nchunk_cols, count), 256, 0, st>>>(
+				k_rows_times_range<false, 8><<<dim3((r_hi - r_mid) / 4, nchunk_cols, count), 256, 0, st>>>(
 				    L, (long long)m->mat, m->npad, r_mid, r_lo, r_mid, UG, sUG, nullptr, bsrc, bstride, bcomp, m->ncp, AB, sUG);
 		}
 	}
@@ -661,7 +661,7 @@ static void run_wt_times(emub_model *m, cudaStream_t st, int s0, int count, int 
 	const long long sUG = (long long)m->npad * m->ncp;
 	LaunchScope ls(m->ctx, EMUB_K_SKINNY, count * 4.0 * (double)m->mat * (nchunk_cols ? nchunk_cols : 1), st);
 	if (nchunk_cols == 0) {
-		k_cols_times<true, 1><<<dim3(m->npad / 32, 1, count), 256, 0, st>>>(
+		k_cols_times<true, 1><<<dim3(m->npad / 32, 1, count), COLS_TIMES_WARPS(1) * 32, 0, st>>>(
 		    m->bufW + (size_t)s0 * m->mat, (long long)m->mat, m->npad, m->npad, m->dUG + (size_t)s0 * sUG, sUG, m->ncp,
 		    m->dAB + (size_t)s0 * sUG, sUG);
 		return;

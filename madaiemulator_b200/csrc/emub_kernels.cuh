@@ -208,25 +208,28 @@ __global__ void k_pad_identity(double *__restrict__ A, int npad, int n)
 }
 
 // ---- skinny products ---------------------------------------------------------------------------------
-// (a) rows [r_lo, r_lo + 32 gridDim.x) of   OUT = [S -] M[:, j_lo:j_hi) V[j_lo:j_hi)   on 8 columns c0..c0+8 of V:
+// (a) rows [r_lo, r_lo + 4 gridDim.x) of   OUT = [S -] M[:, j_lo:j_hi) V[j_lo:j_hi)   on columns c0.. of V:
 //     TRI:  acc(i) = sum_{j in [j_lo, min(i, j_hi - 1)]} M[i][j] V[j]     (M = W lower triangular; OUT = acc)
 //     else: acc(i) = sum_{j in [j_lo, j_hi)} M[i][j] V[j]                  (M = L21; OUT = S - acc when S is given)
 // These are the two steps of the block forward substitution L u = [y | H] (emub_api.cu: run_regression).
-// grid (nrows/32, ncp/8, B), 256 threads: one warp per 4 rows, lanes stride over the columns j.
+// grid (nrows/4, ncp/8, B), 256 threads: a CTA owns 4 rows, its 8 warps take the columns in interleaved slices of 32
+// (warp w: j_lo + 32 w + lane + 256 t), the 8 partial sums meet in shared memory and are added in warp order -- a fixed
+// order, so the result does not depend on the batch or on timing.  Four rows per CTA keeps a single matrix (B = 1, the
+// reference's own restart loop through the glue) spread over the whole GPU: 512 CTAs for the 2048-row step at n = 4096.
 // V (and S) of slot b: base + comp[b] * stride when comp is given (the training vector / PCA component the slot
 // evaluates, shared by all slots), else base + b * stride (per-slot buffer).
 // NC = 8: eight columns per CTA column chunk (blockIdx.y); NC = 2: the first two columns only -- y and the constant
-// regression function, all there is for regression order 0 -- a quarter of the V traffic and of the multiply-adds
-// (V comes through L1/L2 at 64 bytes per lane and step with NC = 8, twice the bytes of the HBM stream of M).
+// regression function, all there is for regression order 0 -- a quarter of the V traffic and of the multiply-adds.
 template <bool TRI, int NC>
 __global__ void __launch_bounds__(256) k_rows_times_range(const double *__restrict__ Mbase, long long strideM, int ld, int r_lo,
                                                           int j_lo, int j_hi, const double *__restrict__ Vbase, long long strideV,
                                                           const int *__restrict__ compV, const double *Sbase, long long strideS,
                                                           const int *__restrict__ compS, int ncp, double *Obase, long long strideO)
 {
+	__shared__ double red[8][4][NC];
 	const int b = blockIdx.z, c0 = blockIdx.y * 8;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int r0 = r_lo + blockIdx.x * 32 + warp * 4;
+	const int r0 = r_lo + blockIdx.x * 4;
 	const double *M = Mbase + b * strideM;
 	const double *V = Vbase + (compV ? compV[b] : b) * strideV;
 	double acc[4][NC];
@@ -235,7 +238,8 @@ __global__ void __launch_bounds__(256) k_rows_times_range(const double *__restri
 #pragma unroll
 		for (int c = 0; c < NC; c++) acc[r][c] = 0.0;
 	const int jmax = TRI ? min(r0 + 3, j_hi - 1) : j_hi - 1;
-	for (int j = j_lo + lane; j <= jmax; j += 32) {
+#pragma unroll 2
+	for (int j = j_lo + warp * 32 + lane; j <= jmax; j += 256) {
 		double v[NC];
 		if (NC == 2) {
 			const double2 v0 = *reinterpret_cast<const double2 *>(V + (size_t)j * ncp + c0);
@@ -260,34 +264,39 @@ __global__ void __launch_bounds__(256) k_rows_times_range(const double *__restri
 			double s = acc[r][c];
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-			acc[r][c] = s;
+			if (lane == 0) red[warp][r][c] = s;
 		}
-	if (lane < 4) {
-		double *O = Obase + b * strideO + (size_t)(r0 + lane) * ncp + c0;
-		const double *S = Sbase ? Sbase + (compS ? compS[b] : b) * strideS + (size_t)(r0 + lane) * ncp + c0 : nullptr;
+	__syncthreads();
+	if (threadIdx.x < 4 * NC) {
+		const int r = threadIdx.x / NC, c = threadIdx.x % NC;
+		double s = 0.0;
 #pragma unroll
-		for (int r = 0; r < 4; r++)
-			if (lane == r) {
+		for (int w = 0; w < 8; w++) s += red[w][r][c];
+		double *O = Obase + b * strideO + (size_t)(r0 + r) * ncp + c0;
+		if (Sbase) s = Sbase[(compS ? compS[b] : b) * strideS + (size_t)(r0 + r) * ncp + c0 + c] - s;
+		O[c] = s;
+		// the columns this instantiation skips are structural zeros of Yh
+		if (NC < 8 && !Sbase && c == 0)
 #pragma unroll
-				for (int c = 0; c < NC; c++) O[c] = S ? S[c] - acc[r][c] : acc[r][c];
-				// the columns this instantiation skips are structural zeros of Yh
-				if (NC < 8 && !S)
-#pragma unroll
-					for (int c = NC; c < 8; c++) O[c] = 0.0;
-			}
+			for (int cc = NC; cc < 8; cc++) O[cc] = 0.0;
 	}
 }
 
 // (b) OUT[j][c0..c0+8) = sum_{i >= ibegin(j)} M[i][j] * V[i][c0..c0+8)
 // TRI: M = W lower triangular (i >= j); otherwise all nrows rows (M = K, n x mq).
 // grid (ncols/32, ncp/8, B), 256 threads: lanes = 32 consecutive columns, warps stride over rows.
-// NC = 8: the eight columns c0..c0+8 of V; NC = 1: column 0 only (alpha = W^T u, all the literal gradient reads of AB)
+// NC = 8: the eight columns c0..c0+8 of V, 8 warps; NC = 1: column 0 only (alpha = W^T u, all the literal gradient
+// reads of AB), 16 warps -- twice the rows in flight per column block, which is what a single matrix (B = 1) needs.
+// Launch with COLS_TIMES_WARPS(NC) * 32 threads.
+#define COLS_TIMES_WARPS(NC) ((NC) == 1 ? 16 : 8)
 template <bool TRI, int NC = 8>
-__global__ void __launch_bounds__(256) k_cols_times(const double *__restrict__ Mbase, long long strideM, int ld, int nrows,
-                                                    const double *__restrict__ Vbase, long long strideV, int ncp,
-                                                    double *__restrict__ Obase, long long strideO)
+__global__ void __launch_bounds__(COLS_TIMES_WARPS(NC) * 32) k_cols_times(const double *__restrict__ Mbase, long long strideM, int ld,
+                                                                         int nrows, const double *__restrict__ Vbase,
+                                                                         long long strideV, int ncp, double *__restrict__ Obase,
+                                                                         long long strideO)
 {
-	__shared__ double red[8][32][NC + 1];
+	constexpr int NW = COLS_TIMES_WARPS(NC);
+	__shared__ double red[NW][32][NC + 1];
 	const int b = blockIdx.z, c0 = blockIdx.y * 8;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int j0 = blockIdx.x * 32, j = j0 + lane;
@@ -299,14 +308,14 @@ __global__ void __launch_bounds__(256) k_cols_times(const double *__restrict__ M
 	const int ibeg = TRI ? j0 : 0;
 	if (NC == 1) {
 #pragma unroll 8
-		for (int i = ibeg + warp; i < nrows; i += 8) {
+		for (int i = ibeg + warp; i < nrows; i += NW) {
 			double m = M[(size_t)i * ld + j];
 			if (TRI && i < j) m = 0.0;
 			acc[0] += m * V[(size_t)i * ncp + c0];
 		}
 	} else {
 #pragma unroll 4
-		for (int i = ibeg + warp; i < nrows; i += 8) {
+		for (int i = ibeg + warp; i < nrows; i += NW) {
 			double m = M[(size_t)i * ld + j];
 			if (TRI && i < j) m = 0.0;
 			const double4 v0 = *reinterpret_cast<const double4 *>(V + (size_t)i * ncp + c0);
@@ -322,14 +331,14 @@ __global__ void __launch_bounds__(256) k_cols_times(const double *__restrict__ M
 		if (threadIdx.x < 32) {
 			double s = 0.0;
 #pragma unroll
-			for (int w = 0; w < 8; w++) s += red[w][threadIdx.x][0];
+			for (int w = 0; w < NW; w++) s += red[w][threadIdx.x][0];
 			Obase[b * strideO + (size_t)(j0 + threadIdx.x) * ncp + c0] = s;
 		}
 	} else {
 		const int l = threadIdx.x >> 3, c = threadIdx.x & 7;
 		double s = 0.0;
 #pragma unroll
-		for (int w = 0; w < 8; w++) s += red[w][l][c % NC];
+		for (int w = 0; w < NW; w++) s += red[w][l][c % NC];
 		Obase[b * strideO + (size_t)(j0 + l) * ncp + c0 + c] = s;
 	}
 }
