@@ -58,12 +58,18 @@ static const char *k_family_names[EMUB_K_NFAMILIES] = {"cov", "potf2", "gemm_cho
                                                        "small", "grad", "kcross", "gemm_pred", "pred_final"};
 
 struct ProfAcc { double ms; long long launches; double work; };
+constexpr int AUX_DEPTH = 12;
 
 struct emub_ctx {
 	int device;
 	int ngroups;
 	int use_graphs;  // replay captured CUDA graphs for the per-chunk launch sequences (default on; EMUB_NO_GRAPHS=1 disables)
 	cudaStream_t streams[4];
+	// side streams of the factorisation, per group and recursion depth: the first product of a node's inverse merge
+	// (T = L21 W11) is independent of everything its right child does, so with few matrices in flight it runs beside it
+	cudaStream_t aux[4][AUX_DEPTH];
+	cudaEvent_t aux_fork[4][AUX_DEPTH], aux_join[4][AUX_DEPTH];
+	int aux_max_count;  // use the side streams when a group holds at most this many matrices (EMUB_AUX_MAX, default 8; 0 = never)
 	int profile;
 	ProfAcc prof[EMUB_K_NFAMILIES];
 	long long launches;
@@ -96,7 +102,7 @@ struct LaunchScope {
 
 // one kernel launch of the factorisation sequence (depth-first order of the recursion)
 enum { STEP_POTF2 = 0, STEP_TRSM, STEP_SYRK, STEP_TMUL, STEP_WMUL };
-struct FactorStep { int type; int off, cnt; int kblk; double flops; int full_only; };
+struct FactorStep { int type; int off, cnt; int kblk; double flops; int full_only; int depth; };
 // a node [lo, hi) of the recursion on its right spine (root, right child of the root, ...), split at mid
 struct SpineNode { int lo, mid, hi; };
 
@@ -181,9 +187,18 @@ extern "C" int emub_ctx_create(int device, emub_ctx **out)
 	c->use_graphs = getenv("EMUB_NO_GRAPHS") ? 0 : 1;
 	// half of what the default configuration keeps resident (148 SMs x 4 CTAs)
 	c->small_launch_ctas = getenv("EMUB_SMALL_CTAS") ? atoll(getenv("EMUB_SMALL_CTAS")) : 296;
+	c->aux_max_count = getenv("EMUB_AUX_MAX") ? atoi(getenv("EMUB_AUX_MAX")) : 8;
+	int prio_lo = 0, prio_hi = 0;
+	CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
 	for (int g = 0; g < 4; g++) {
-		CUDA_TRY(cudaStreamCreateWithFlags(&c->streams[g], cudaStreamNonBlocking));
+		// the main stream of a group carries the critical path (leaf factorisations, TRSM, SYRK): highest priority
+		CUDA_TRY(cudaStreamCreateWithPriority(&c->streams[g], cudaStreamNonBlocking, prio_hi));
 		CUDA_TRY(cudaEventCreateWithFlags(&c->gev[g], cudaEventDisableTiming));
+		for (int k = 0; k < AUX_DEPTH; k++) {
+			CUDA_TRY(cudaStreamCreateWithPriority(&c->aux[g][k], cudaStreamNonBlocking, prio_lo));
+			CUDA_TRY(cudaEventCreateWithFlags(&c->aux_fork[g][k], cudaEventDisableTiming));
+			CUDA_TRY(cudaEventCreateWithFlags(&c->aux_join[g][k], cudaEventDisableTiming));
+		}
 	}
 	CUDA_TRY(cudaEventCreate(&c->ev0));
 	CUDA_TRY(cudaEventCreate(&c->ev1));
@@ -222,7 +237,15 @@ extern "C" void emub_ctx_destroy(emub_ctx *c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaDeviceSynchronize();
-	for (int g = 0; g < 4; g++) { cudaStreamDestroy(c->streams[g]); cudaEventDestroy(c->gev[g]); }
+	for (int g = 0; g < 4; g++) {
+		cudaStreamDestroy(c->streams[g]);
+		cudaEventDestroy(c->gev[g]);
+		for (int k = 0; k < AUX_DEPTH; k++) {
+			cudaStreamDestroy(c->aux[g][k]);
+			cudaEventDestroy(c->aux_fork[g][k]);
+			cudaEventDestroy(c->aux_join[g][k]);
+		}
+	}
 	cudaEventDestroy(c->ev0);
 	cudaEventDestroy(c->ev1);
 	delete c;
@@ -244,7 +267,7 @@ extern "C" int emub_ctx_synchronize(emub_ctx *c)
 {
 	if (!c) return EMUB_EINVAL;
 	CUDA_TRY(cudaSetDevice(c->device));
-	for (int g = 0; g < 4; g++) CUDA_TRY(cudaStreamSynchronize(c->streams[g]));
+	for (int g = 0; g < 4; g++) CUDA_TRY(cudaStreamSynchronize(c->streams[g]));  // the side streams join their main stream
 	return EMUB_OK;
 }
 extern "C" int emub_profile_enable(emub_ctx *c, int on) { if (!c) return EMUB_EINVAL; c->profile = on ? 1 : 0; return EMUB_OK; }
@@ -274,41 +297,43 @@ extern "C" long long emub_launch_count(emub_ctx *c) { return c ? c->launches : 0
 // full inverse uses.  Those steps are marked full_only: a value-only likelihood (evalFnMulti, maxmultimin.c:288-394)
 // skips them and costs n^3/3 + n^3/21 flops instead of 2n^3/3 (+ n^3/3 for W^T W); L and the W blocks it does build are
 // the same bits either way.
-static void build_factor(emub_model *m, int lo, int hi, std::vector<GemmTask> &tasks, bool on_spine)
+static void build_factor(emub_model *m, int lo, int hi, std::vector<GemmTask> &tasks, bool on_spine, int depth = 0)
 {
 	const long long ld = m->npad;
 	auto off = [&](int bi, int bj) { return (long long)bi * TB * ld + (long long)bj * TB; };
 	auto by_k = [](const GemmTask &a, const GemmTask &b) { return a.klen > b.klen; };
 	auto emit = [&](int type, std::vector<GemmTask> &t, int full_only) {
 		std::stable_sort(t.begin(), t.end(), by_k);
-		FactorStep st{type, (int)tasks.size(), (int)t.size(), 0, 0.0, full_only};
+		FactorStep st{type, (int)tasks.size(), (int)t.size(), 0, 0.0, full_only, depth};
 		for (auto &x : t) { tasks.push_back(x); st.flops += task_flops(x); }
 		m->steps.push_back(st);
 	};
 	if (hi - lo == 1) {
-		m->steps.push_back({STEP_POTF2, 0, 0, lo, 2.0 * TB * TB * TB / 3.0, 0});
+		m->steps.push_back({STEP_POTF2, 0, 0, lo, 2.0 * TB * TB * TB / 3.0, 0, depth});
 		if (on_spine) m->spine.push_back({lo, hi, hi});
 		return;
 	}
 	const int mid = lo + (hi - lo + 1) / 2;
 	if (on_spine) m->spine.push_back({lo, mid, hi});
-	build_factor(m, lo, mid, tasks, false);
+	build_factor(m, lo, mid, tasks, false, depth + 1);
 	std::vector<GemmTask> t;
 	// L(i,j) = sum_{k in [lo, j]} A(i,k) W(j,k)^T          A = bufA KMAJOR, B = bufW KMAJOR -> bufT
 	for (int i = mid; i < hi; i++)
 		for (int j = lo; j < mid; j++) t.push_back({off(i, lo), off(j, lo), off(i, j), (j - lo + 1) * TB, TASK_TRIM_END_SC0});
 	emit(STEP_TRSM, t, 0);
 	t.clear();
+	// T(i,j) = sum_{k in [j, mid)} L(i,k) W(k,j)           A = bufT KMAJOR, B = bufW RMAJOR -> bufA
+	// Issued right after the TRSM: it needs L21 and W11 only and writes the A21 region of bufA, which nothing reads any
+	// more, so it is independent of the SYRK and of the whole right child -- run_factor puts it on a side stream.
+	for (int i = mid; i < hi; i++)
+		for (int j = lo; j < mid; j++) t.push_back({off(i, j), off(j, j), off(i, j), (mid - j) * TB, TASK_TRIM_BEGIN_SC1});
+	emit(STEP_TMUL, t, on_spine ? 1 : 0);
+	t.clear();
 	// A(i,j) -= sum_{k in [lo, mid)} L(i,k) L(j,k)^T      A, B = bufT KMAJOR -> bufA
 	for (int i = mid; i < hi; i++)
 		for (int j = mid; j <= i; j++) t.push_back({off(i, lo), off(j, lo), off(i, j), (mid - lo) * TB, (i == j) ? TASK_LOWER : 0});
 	emit(STEP_SYRK, t, 0);
-	build_factor(m, mid, hi, tasks, on_spine);
-	t.clear();
-	// T(i,j) = sum_{k in [j, mid)} L(i,k) W(k,j)           A = bufT KMAJOR, B = bufW RMAJOR -> bufA
-	for (int i = mid; i < hi; i++)
-		for (int j = lo; j < mid; j++) t.push_back({off(i, j), off(j, j), off(i, j), (mid - j) * TB, TASK_TRIM_BEGIN_SC1});
-	emit(STEP_TMUL, t, on_spine ? 1 : 0);
+	build_factor(m, mid, hi, tasks, on_spine, depth + 1);
 	t.clear();
 	// W(i,j) = - sum_{k in [mid, i]} W(i,k) T(k,j)         A = bufW KMAJOR, B = bufA RMAJOR -> bufW
 	for (int i = mid; i < hi; i++)
@@ -566,10 +591,14 @@ static void run_factor(emub_model *m, cudaStream_t st, int s0, int nslots, int n
 	const int ld = m->npad;
 	const long long ms = (long long)m->mat;
 	double *A = m->bufA + (size_t)s0 * m->mat, *W = m->bufW + (size_t)s0 * m->mat, *T = m->bufT + (size_t)s0 * m->mat;
+	int g = 0;
+	for (int k = 0; k < 4; k++) if (c->streams[k] == st) g = k;
+	const bool side = !c->profile && nslots <= c->aux_max_count;
 	for (const FactorStep &s : m->steps) {
 		const int count = s.full_only ? nfull : nslots;
 		if (count <= 0) continue;
 		const GemmTask *tk = m->dTasks + s.off;
+		const bool aux = side && s.depth < AUX_DEPTH;
 		switch (s.type) {
 		case STEP_POTF2: {
 			LaunchScope ls(c, EMUB_K_POTF2, count * s.flops, st);
@@ -584,9 +613,16 @@ static void run_factor(emub_model *m, cudaStream_t st, int s0, int nslots, int n
 			launch_gemm<KMAJOR, KMAJOR, EPI_SUB>(c, EMUB_K_GEMM_CHOL, s.flops, st, tk, s.cnt, count, T, ms, ld, T, ms, ld, A, ms, ld, 1.0);
 			break;
 		case STEP_TMUL:
-			launch_gemm<KMAJOR, RMAJOR, EPI_STORE>(c, EMUB_K_GEMM_TRTRI, s.flops, st, tk, s.cnt, count, T, ms, ld, W, ms, ld, A, ms, ld, 1.0);
+			if (aux) {
+				cudaEventRecord(c->aux_fork[g][s.depth], st);  // after the node's TRSM
+				cudaStreamWaitEvent(c->aux[g][s.depth], c->aux_fork[g][s.depth], 0);
+				launch_gemm<KMAJOR, RMAJOR, EPI_STORE>(c, EMUB_K_GEMM_TRTRI, s.flops, c->aux[g][s.depth], tk, s.cnt, count, T, ms, ld, W, ms, ld, A, ms, ld, 1.0);
+				cudaEventRecord(c->aux_join[g][s.depth], c->aux[g][s.depth]);
+			} else
+				launch_gemm<KMAJOR, RMAJOR, EPI_STORE>(c, EMUB_K_GEMM_TRTRI, s.flops, st, tk, s.cnt, count, T, ms, ld, W, ms, ld, A, ms, ld, 1.0);
 			break;
 		case STEP_WMUL:
+			if (aux) cudaStreamWaitEvent(st, c->aux_join[g][s.depth], 0);  // T of this node
 			launch_gemm<KMAJOR, RMAJOR, EPI_STORE>(c, EMUB_K_GEMM_TRTRI, s.flops, st, tk, s.cnt, count, W, ms, ld, A, ms, ld, W, ms, ld, -1.0);
 			break;
 		}
