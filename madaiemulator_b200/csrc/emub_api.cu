@@ -1336,7 +1336,10 @@ static int predict_chunk(emub_emulator *e, cudaStream_t st, const double *dQ, in
 	{
 		const int nchunk_cols = (m->p + 1 + 7) / 8;
 		LaunchScope ls(c, EMUB_K_SKINNY, 8.0 * (double)m->npad * mq_pad * nchunk_cols, st);
-		k_cols_times<false><<<dim3(mq_pad / 32, nchunk_cols, 1), 256, 0, st>>>(w->dK, 0, ldk, m->npad, e->AB, 0, m->ncp, w->dKA, 0);
+		if (m->p + 1 <= 2)  // regression order 0: K^T [a | C^-1 1]; k_pred_final reads the first p + 1 columns of KA only
+			k_cols_times<false, 2><<<dim3(mq_pad / 32, 1, 1), COLS_TIMES_WARPS(2) * 32, 0, st>>>(w->dK, 0, ldk, m->npad, e->AB, 0, m->ncp, w->dKA, 0);
+		else
+			k_cols_times<false><<<dim3(mq_pad / 32, nchunk_cols, 1), 256, 0, st>>>(w->dK, 0, ldk, m->npad, e->AB, 0, m->ncp, w->dKA, 0);
 	}
 	{
 		LaunchScope ls(c, EMUB_K_PRED_FINAL, 0, st);

@@ -286,9 +286,10 @@ __global__ void __launch_bounds__(256) k_rows_times_range(const double *__restri
 // TRI: M = W lower triangular (i >= j); otherwise all nrows rows (M = K, n x mq).
 // grid (ncols/32, ncp/8, B), 256 threads: lanes = 32 consecutive columns, warps stride over rows.
 // NC = 8: the eight columns c0..c0+8 of V, 8 warps; NC = 1: column 0 only (alpha = W^T u, all the literal gradient
-// reads of AB), 16 warps -- twice the rows in flight per column block, which is what a single matrix (B = 1) needs.
+// reads of AB); NC = 2: columns 0 and 1 ([a | C^-1 1], all there is for regression order 0) -- 16 warps each: twice the
+// rows in flight per column block, which is what a single matrix (B = 1) needs.
 // Launch with COLS_TIMES_WARPS(NC) * 32 threads.
-#define COLS_TIMES_WARPS(NC) ((NC) == 1 ? 16 : 8)
+#define COLS_TIMES_WARPS(NC) ((NC) <= 2 ? 16 : 8)
 template <bool TRI, int NC = 8>
 __global__ void __launch_bounds__(COLS_TIMES_WARPS(NC) * 32) k_cols_times(const double *__restrict__ Mbase, long long strideM, int ld,
                                                                          int nrows, const double *__restrict__ Vbase,
@@ -313,6 +314,14 @@ __global__ void __launch_bounds__(COLS_TIMES_WARPS(NC) * 32) k_cols_times(const 
 			if (TRI && i < j) m = 0.0;
 			acc[0] += m * V[(size_t)i * ncp + c0];
 		}
+	} else if (NC == 2) {
+#pragma unroll 8
+		for (int i = ibeg + warp; i < nrows; i += NW) {
+			double m = M[(size_t)i * ld + j];
+			if (TRI && i < j) m = 0.0;
+			const double2 v = *reinterpret_cast<const double2 *>(V + (size_t)i * ncp + c0);
+			acc[0] += m * v.x; acc[1 % NC] += m * v.y;
+		}
 	} else {
 #pragma unroll 4
 		for (int i = ibeg + warp; i < nrows; i += NW) {
@@ -333,6 +342,14 @@ __global__ void __launch_bounds__(COLS_TIMES_WARPS(NC) * 32) k_cols_times(const 
 #pragma unroll
 			for (int w = 0; w < NW; w++) s += red[w][threadIdx.x][0];
 			Obase[b * strideO + (size_t)(j0 + threadIdx.x) * ncp + c0] = s;
+		}
+	} else if (NC == 2) {
+		if (threadIdx.x < 64) {
+			const int l = threadIdx.x >> 1, c = threadIdx.x & 1;
+			double s = 0.0;
+#pragma unroll
+			for (int w = 0; w < NW; w++) s += red[w][l][c % NC];
+			Obase[b * strideO + (size_t)(j0 + l) * ncp + c0 + c] = s;
 		}
 	} else {
 		const int l = threadIdx.x >> 3, c = threadIdx.x & 7;
