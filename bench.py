@@ -280,14 +280,7 @@ def strong_section(engine, ds, ctx, rank, world, local, barrier, max_over_ranks)
 
     def gather_rows(local_rows, counts):
         """all_gather of per-rank row blocks: the final gather of thetas / predictions, the only cross-rank traffic"""
-        if world == 1:
-            return [local_rows]
-        pad = np.zeros((max(counts), local_rows.shape[1]))
-        pad[:local_rows.shape[0]] = local_rows
-        t = torch.from_numpy(pad).to(dev)
-        outs = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(outs, t)
-        return [o.cpu().numpy()[:c] for o, c in zip(outs, counts)]
+        return sharding.gather_row_blocks(local_rows, counts, device=dev if world > 1 else None)
 
     out = {}
     identical = {}
@@ -343,9 +336,7 @@ def strong_section(engine, ds, ctx, rank, world, local, barrier, max_over_ranks)
     (th_loc, best_loc, st), t_sh, wall_sh, slots = train(mine, rank, world, True)
     counts = [len(sharding.round_robin(CFG4_COMPONENTS, world, r)) for r in range(world)]
     blocks = gather_rows(np.column_stack([th_loc, best_loc]), counts)
-    gathered = np.zeros((CFG4_COMPONENTS, nth + 1))
-    for r in range(world):
-        gathered[sharding.round_robin(CFG4_COMPONENTS, world, r)] = blocks[r]
+    gathered = sharding.scatter_round_robin(blocks, CFG4_COMPONENTS)
     evals = np.array([float(st["evaluations"]), float(st["batches"]), float(st["value_evaluations"])])
     if world > 1:
         t = torch.from_numpy(evals).to(dev)

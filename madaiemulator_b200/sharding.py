@@ -43,6 +43,36 @@ def shard_map_rows(fn, rows, group=None, device=None):
     return np.concatenate([o.cpu().numpy()[:h - l] for o, (l, h) in zip(outs, sizes)], axis=0)
 
 
+def gather_row_blocks(local_rows, counts, group=None, device=None):
+    """The final gather of a sharded job: every rank contributes a (counts[rank] x k) block of rows (its thetas, its
+    block of predictions); returns the list of all ranks' blocks on every rank.  The only cross-rank traffic of the
+    path; NCCL on the GPUs (pass device), gloo in the CPU tests."""
+    import torch
+    import torch.distributed as dist
+    local_rows = np.ascontiguousarray(local_rows, dtype=np.float64).reshape(len(local_rows), -1)
+    if not (dist.is_available() and dist.is_initialized()):
+        return [local_rows]
+    world = dist.get_world_size(group)
+    pad = np.zeros((max(max(counts), 1), local_rows.shape[1]))
+    pad[:local_rows.shape[0]] = local_rows
+    t = torch.from_numpy(pad)
+    if device is not None:
+        t = t.to(device)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    return [o.cpu().numpy()[:c] for o, c in zip(outs, counts)]
+
+
+def scatter_round_robin(blocks, n_items):
+    """Undo round_robin: blocks[r] holds the rows of the items rank r owns; returns them in item order."""
+    world = len(blocks)
+    k = blocks[0].shape[1]
+    out = np.zeros((n_items, k))
+    for r in range(world):
+        out[round_robin(n_items, world, r)] = blocks[r]
+    return out
+
+
 def max_over_ranks(x, group=None, device=None):
     import torch
     import torch.distributed as dist

@@ -40,10 +40,19 @@ def _worker(rank, world, port, q):
 
     full = sharding.shard_map_rows(evaluate, thetas)
     t = sharding.max_over_ranks(1.0 + rank)
+    # the strong-scaling jobs of bench.py: components round-robin over ranks, query points in contiguous blocks
+    ncomp = 5
+    mine = sharding.round_robin(ncomp, world, rank)
+    blocks = sharding.gather_row_blocks(np.array([[10.0 * c, c + 0.5] for c in mine]).reshape(len(mine), 2),
+                                        [len(sharding.round_robin(ncomp, world, r)) for r in range(world)])
+    comps = sharding.scatter_round_robin(blocks, ncomp)
+    lo, hi = sharding.block_range(11, world, rank)
+    qblocks = sharding.gather_row_blocks(np.arange(lo, hi, dtype=np.float64)[:, None] ** 2,
+                                         [b - a for a, b in (sharding.block_range(11, world, r) for r in range(world))])
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        q.put((full, t, np.array([evaluate(thetas[i:i + 1])[0] for i in range(7)])))
+        q.put((full, t, np.array([evaluate(thetas[i:i + 1])[0] for i in range(7)]), comps, np.concatenate(qblocks)[:, 0]))
 
 
 def test_block_ranges_cover_everything():
@@ -64,10 +73,12 @@ def test_shard_map_two_ranks_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    full, t, serial = q.get(timeout=120)
+    full, t, serial, comps, qall = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert full.shape == (7, 4)
     assert np.array_equal(full, serial)
     assert t == 2.0
+    assert np.array_equal(comps, np.array([[10.0 * c, c + 0.5] for c in range(5)]))
+    assert np.array_equal(qall, np.arange(11.0) ** 2)
