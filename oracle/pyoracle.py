@@ -187,6 +187,11 @@ class RefOracle:
                 L.ref_model_ranges_ex.argtypes = [_vp, _ci, _ci, ctypes.c_double, _dp]
                 L.ref_model_ranges_ex.restype = None
             L.ref_cov_matrix.argtypes = [_vp, _dp, _dp]
+            if hasattr(L, "ref_k_vector"):
+                L.ref_k_vector.argtypes = [_vp, _dp, _dp, _dp]
+                L.ref_k_vector.restype = None
+                L.ref_chol_inverse.argtypes = [_vp, _dp, _dp, _dp]
+                L.ref_chol_inverse.restype = None
             L.ref_cov_pair.restype = ctypes.c_double
             L.ref_cov_pair.argtypes = [_vp, _dp, _dp, _dp]
             L.ref_deriv_matrix.argtypes = [_vp, ctypes.c_double, _ci, _dp]
@@ -240,6 +245,20 @@ class RefOracle:
 
     def cov_pair(self, xa, xb, thetas):
         return self.L.ref_cov_pair(self.h, _P(_c(xa)), _P(_c(xb)), _P(_c(thetas)))
+
+    def k_vector(self, thetas, xnew):
+        """makeKVector_fnptr (emulator.c:578)"""
+        k = np.empty(self.n)
+        self.L.ref_k_vector(self.h, _P(_c(thetas)), _P(_c(xnew)), _P(k))
+        return k
+
+    def chol_inverse(self, A):
+        """chol_inverse_cov_matrix (emulate-fns.c:275): (inverse, determinant) of an n x n matrix"""
+        A = _c(A)
+        out = np.empty_like(A)
+        det = ctypes.c_double()
+        self.L.ref_chol_inverse(self.h, _P(A), _P(out), ctypes.byref(det))
+        return out, det.value
 
     def deriv_matrix(self, theta_length, index):
         D = np.empty((self.n, self.n))

@@ -142,6 +142,32 @@ void ref_cov_matrix(void *h, const double *thetas, double *C_out)
 	                    r->model->covariance_fn);
 }
 
+/* -> makeKVector_fnptr, src/libEmu/emulator.c:578 (1e-10 clamp :588-590); k_out has nmodel_points entries */
+void ref_k_vector(void *h, const double *thetas, const double *xnew, double *k_out)
+{
+	ref_model *r = (ref_model *)h;
+	optstruct *o = r->model->options;
+	gsl_vector_view tv = gsl_vector_view_array((double *)thetas, o->nthetas);
+	gsl_vector_view xv = gsl_vector_view_array((double *)xnew, o->nparams);
+	gsl_vector_view kv = gsl_vector_view_array(k_out, o->nmodel_points);
+	makeKVector_fnptr(&kv.vector, r->model->xmodel, &xv.vector, &tv.vector, o->nmodel_points, o->nthetas, o->nparams,
+	                  r->model->covariance_fn);
+}
+
+/* -> chol_inverse_cov_matrix, src/libEmu/emulate-fns.c:275: A (n x n, destroyed by the reference: pass a copy) ->
+ * inverse and determinant */
+void ref_chol_inverse(void *h, const double *A, double *Ainv_out, double *det_out)
+{
+	ref_model *r = (ref_model *)h;
+	optstruct *o = r->model->options;
+	const int n = o->nmodel_points;
+	gsl_matrix *tmp = gsl_matrix_alloc(n, n);
+	memcpy(tmp->data, A, sizeof(double) * (size_t)n * n);
+	gsl_matrix_view out = gsl_matrix_view_array(Ainv_out, n, n);
+	chol_inverse_cov_matrix(o, tmp, &out.matrix, det_out);
+	gsl_matrix_free(tmp);
+}
+
 /* one covariance value -> model->covariance_fn (covariance_fn_gaussian :101 / matern :344,:438) */
 double ref_cov_pair(void *h, const double *xa, const double *xb, const double *thetas)
 {

@@ -64,6 +64,29 @@ def test_point_list_entry_points_run_on_the_engine(oracles, name):
     assert relerr(m3, m2[:5], 1e-3) < 1e-11 and np.max(np.abs(v3 - v2[:5])) < 1e-11 * max(1.0, float(c["kappa"]))
 
 
+@pytest.mark.parametrize("name", ["uni-simple-o1", "multi-simple-pc0-o1", "multi-simple-m52"])
+def test_lower_level_symbols_run_on_the_engine(oracles, name):
+    """makeKVector_fnptr (emulator.c:578) and chol_inverse_cov_matrix (emulate-fns.c:275) through the glue: the k-vector
+    incl. the 1e-10 clamp and a query on a design point; inverse + determinant of the covariance matrix."""
+    po = oracles
+    c = load_golden(name)
+    ref = po.RefOracle(c["X"], c["y"], c["kernel"], c["order"])
+    dro = po.DropinOracle(c["X"], c["y"], c["kernel"], c["order"])
+    th = c["theta_full"]
+    for x in (c["pts"][0], c["pts"][3], c["X"][2], c["X"][0] + 50.0):  # far away: every entry clamps to 0
+        k_ref, k_dro = ref.k_vector(th, x), dro.k_vector(th, x)
+        assert relerr(k_dro, k_ref, 1e-300) < 1e-9
+        assert np.array_equal(k_dro == 0.0, k_ref == 0.0)
+    C = ref.cov_matrix(th)
+    inv_ref, det_ref = ref.chol_inverse(C)
+    inv_dro, det_dro = dro.chol_inverse(C)
+    assert np.max(np.abs(inv_dro - inv_ref)) < 1e-9 * np.max(np.abs(inv_ref))
+    assert np.array_equal(inv_dro, inv_dro.T)
+    if det_ref > 0 and np.isfinite(det_ref):
+        assert relerr(det_dro, det_ref) < 1e-9
+    assert abs(np.log(det_dro) - np.linalg.slogdet(C)[1]) < 1e-9 * max(1.0, abs(np.log(det_dro))) if det_dro > 0 else True
+
+
 def test_glue_recognises_a_model_by_its_contents(oracles):
     """Two models that live at the same addresses one after the other (what the R entry points do: a modelstruct per
     call) must not share an engine copy."""
