@@ -44,6 +44,23 @@ static int set_err(int code, const char *fmt, const char *a = "", int line = 0)
 		if (e__ != cudaSuccess) return set_err(EMUB_ECUDA, "CUDA: %s (emub_api.cu:%d)", cudaGetErrorString(e__), __LINE__); \
 	} while (0)
 
+// Host -> device upload that the kernels of stream `st` may read afterwards.  A plain cudaMemcpy from pageable memory
+// returns once the data sits in the driver's staging buffer (copies up to 64 KB), the DMA itself runs on the legacy
+// default stream -- which the engine's non-blocking streams do not wait for.  A kernel launched right after such a
+// copy can therefore read the destination before the data lands (seen as a model that trained on the previous
+// model's training vector).  Every upload goes through the consumer's stream instead and is completed before the call
+// returns, so that the caller's buffer may be released.
+static cudaError_t upload(void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+	cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+	return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+}
+static cudaError_t upload2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, cudaStream_t st)
+{
+	cudaError_t e = cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyHostToDevice, st);
+	return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+}
+
 // device scratch that lives for one call: released on every return path
 struct ScopedDev {
 	double *p = nullptr;
@@ -400,9 +417,9 @@ extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n,
 	std::vector<double> Xp((size_t)m->npad * d, 0.0);
 	for (int i = 0; i < n; i++) memcpy(&Xp[(size_t)i * d], X + (size_t)i * ldx, sizeof(double) * d);
 	MODEL_TRY(cudaMalloc(&m->dX, Xp.size() * sizeof(double)));
-	MODEL_TRY(cudaMemcpy(m->dX, Xp.data(), Xp.size() * sizeof(double), cudaMemcpyHostToDevice));
+	MODEL_TRY(upload(m->dX, Xp.data(), Xp.size() * sizeof(double), ctx->streams[0]));
 	MODEL_TRY(cudaMalloc(&m->dy, sizeof(double) * n));
-	MODEL_TRY(cudaMemcpy(m->dy, y, sizeof(double) * n, cudaMemcpyHostToDevice));
+	MODEL_TRY(upload(m->dy, y, sizeof(double) * n, ctx->streams[0]));
 	MODEL_TRY(cudaMalloc(&m->dYh, sizeof(double) * (size_t)m->npad * m->ncp));
 	m->ncomp = 1;
 	m->qws = nullptr;
@@ -410,13 +427,15 @@ extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n,
 	build_schedules(m, tasks);
 	if (tasks.empty()) tasks.push_back({0, 0, 0, 0, 0});
 	MODEL_TRY(cudaMalloc(&m->dTasks, tasks.size() * sizeof(GemmTask)));
-	MODEL_TRY(cudaMemcpy(m->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
+	MODEL_TRY(upload(m->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), ctx->streams[0]));
 	const size_t S = slots;
 	MODEL_TRY(cudaMalloc(&m->bufA, S * m->mat * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->bufW, S * m->mat * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->bufT, S * m->mat * sizeof(double)));
-	MODEL_TRY(cudaMemset(m->bufW, 0, S * m->mat * sizeof(double)));
-	MODEL_TRY(cudaMemset(m->bufT, 0, S * m->mat * sizeof(double)));
+	// stream-ordered like every other initialisation (a cudaMemset on the legacy stream is not ordered against the
+	// engine's non-blocking streams and may still run when the first evaluation starts)
+	MODEL_TRY(cudaMemsetAsync(m->bufW, 0, S * m->mat * sizeof(double), ctx->streams[0]));
+	MODEL_TRY(cudaMemsetAsync(m->bufT, 0, S * m->mat * sizeof(double), ctx->streams[0]));
 	MODEL_TRY(cudaMalloc(&m->dUG, S * m->npad * m->ncp * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dAB, S * m->npad * m->ncp * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dConsts, S * CONST_STRIDE * sizeof(double)));
@@ -429,7 +448,7 @@ extern "C" int emub_model_create(emub_ctx *ctx, const double *X, int ldx, int n,
 	MODEL_TRY(cudaMalloc(&m->dThetas, S * (MAXD + 2) * sizeof(double)));
 	MODEL_TRY(cudaMalloc(&m->dInfo, S * sizeof(int)));
 	MODEL_TRY(cudaMalloc(&m->dComp, S * sizeof(int)));
-	MODEL_TRY(cudaMemset(m->dComp, 0, S * sizeof(int)));
+	MODEL_TRY(cudaMemsetAsync(m->dComp, 0, S * sizeof(int), ctx->streams[0]));
 	MODEL_TRY(cudaMallocHost(&m->hComp, S * sizeof(int)));
 	MODEL_TRY(cudaMallocHost(&m->hThetas, S * (MAXD + 2) * sizeof(double)));
 	MODEL_TRY(cudaMallocHost(&m->hRes, S * RES_STRIDE * sizeof(double)));
@@ -499,7 +518,7 @@ extern "C" int emub_model_set_training_multi(emub_model *m, const double *Y, int
 	ScopedDev sY;
 	CUDA_TRY(sY.alloc((size_t)m->n * ncomp));
 	double *dY = sY.p;
-	CUDA_TRY(cudaMemcpy2D(dY, sizeof(double) * ncomp, Y, sizeof(double) * ldy, sizeof(double) * ncomp, m->n, cudaMemcpyHostToDevice));
+	CUDA_TRY(upload2d(dY, sizeof(double) * ncomp, Y, sizeof(double) * ldy, sizeof(double) * ncomp, m->n, st));
 	// captured graphs hold the address of dYh: drop them whenever the training data is rebuilt
 	for (auto &g : m->graphs) cudaGraphExecDestroy(g.second);
 	m->graphs.clear();
@@ -1090,7 +1109,7 @@ extern "C" int emub_debug_exp(emub_ctx *c, const double *x, int n, double *out)
 	CUDA_TRY(sx.alloc((size_t)n));
 	CUDA_TRY(sout.alloc((size_t)n));
 	double *dx = sx.p, *dout = sout.p;
-	CUDA_TRY(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+	CUDA_TRY(upload(dx, x, sizeof(double) * n, c->streams[0]));
 	{
 		LaunchScope ls(c, EMUB_K_SMALL, 0, c->streams[0]);
 		k_debug_exp<<<(n + 255) / 256, 256, 0, c->streams[0]>>>(dx, n, dout);
@@ -1107,7 +1126,7 @@ extern "C" int emub_debug_exp_scaled(emub_ctx *c, const double *x, int n, double
 	ScopedDev sx, sout;
 	CUDA_TRY(sx.alloc((size_t)n));
 	CUDA_TRY(sout.alloc((size_t)n));
-	CUDA_TRY(cudaMemcpy(sx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+	CUDA_TRY(upload(sx.p, x, sizeof(double) * n, c->streams[0]));
 	{
 		LaunchScope ls(c, EMUB_K_SMALL, 0, c->streams[0]);
 		k_debug_exp_scaled<<<(n + 255) / 256, 256, 0, c->streams[0]>>>(sx.p, n, sout.p);
@@ -1187,7 +1206,7 @@ static int build_query_ws(emub_model *m)
 	std::vector<GemmTask> tasks;
 	for (int i = m->nblk - 1; i >= 0; i--) tasks.push_back({(long long)i * TB * m->npad, 0, 0, (i + 1) * TB, i | TASK_TRIM_END_SR0});
 	CUDA_TRY(cudaMalloc(&w->dTasks, tasks.size() * sizeof(GemmTask)));
-	CUDA_TRY(cudaMemcpy(w->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), cudaMemcpyHostToDevice));
+	CUDA_TRY(upload(w->dTasks, tasks.data(), tasks.size() * sizeof(GemmTask), m->ctx->streams[0]));
 	return EMUB_OK;
 }
 
@@ -1663,7 +1682,7 @@ static int predict_multi_impl(emub_emulator *const *emus, int nr, const double *
 		if (h == 0) h = 1;
 		if (h != w->proj_hash) {
 			w->proj_hash = 0;
-			CUDA_TRY(cudaMemcpy(w->dProj, proj.data(), sizeof(double) * proj.size(), cudaMemcpyHostToDevice));
+			CUDA_TRY(upload(w->dProj, proj.data(), sizeof(double) * proj.size(), st));
 			w->proj_hash = h;
 		}
 	}

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <pthread.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -402,6 +403,9 @@ static int estimate_front(emub_model *model, int ncomp, const double *ranges, co
 	int *bcomp = (int *)malloc(sizeof(int) * (size_t)nchains);
 	int *bwant = (int *)malloc(sizeof(int) * (size_t)nchains);
 	int rc = EMUB_OK;
+	FILE *front_log = getenv("EMUB_FRONT_LOG") ? fopen(getenv("EMUB_FRONT_LOG"), "a") : NULL;
+	double *log_buf = NULL;
+	size_t log_len = 0, log_cap = 0;
 	pthread_mutex_lock(&fr.mu);
 	for (;;) {
 		while (fr.nactive > 0 && fr.npending < fr.nactive) pthread_cond_wait(&fr.cv_disp, &fr.mu);
@@ -419,6 +423,16 @@ static int estimate_front(emub_model *model, int ncomp, const double *ranges, co
 		pthread_mutex_unlock(&fr.mu);
 		int call = emub_loglik_grad_batch_mixed(model, bx, bcomp, bwant, B, bf, bg, bs, bst);
 		fr.batches++;
+		if (front_log) { /* EMUB_FRONT_LOG (debugging aid): every batched call kept in memory, written as text when the front ends */
+			const size_t rec = 1 + (size_t)B * (size_t)(fr.nth1 + 5);
+			if (log_len + rec > log_cap) { log_cap = (log_len + rec) * 2; log_buf = (double *)realloc(log_buf, sizeof(double) * log_cap); }
+			log_buf[log_len++] = (double)B;
+			for (int k = 0; k < B; k++) {
+				log_buf[log_len++] = (double)bcomp[k]; log_buf[log_len++] = (double)bwant[k];
+				for (int j = 0; j < fr.nth1; j++) log_buf[log_len++] = bx[(size_t)k * fr.nth1 + j];
+				log_buf[log_len++] = bf[k]; log_buf[log_len++] = bs[k]; log_buf[log_len++] = (double)bst[k];
+			}
+		}
 		pthread_mutex_lock(&fr.mu);
 		if (call != EMUB_OK) { rc = call; fr.failed = 1; }
 		fr.evaluations += B;
@@ -437,6 +451,21 @@ static int estimate_front(emub_model *model, int ncomp, const double *ranges, co
 		pthread_cond_broadcast(&fr.cv_done);
 	}
 	pthread_mutex_unlock(&fr.mu);
+	if (front_log) {
+		for (size_t i = 0; i < log_len;) {
+			const int B = (int)log_buf[i++];
+			fprintf(front_log, "%d\n", B);
+			for (int k = 0; k < B; k++) {
+				fprintf(front_log, "%d %d", (int)log_buf[i], (int)log_buf[i + 1]);
+				i += 2;
+				for (int j = 0; j < fr.nth1; j++) fprintf(front_log, " %.17g", log_buf[i++]);
+				fprintf(front_log, " | %.17g %.17g %d\n", log_buf[i], log_buf[i + 1], (int)log_buf[i + 2]);
+				i += 3;
+			}
+		}
+		fclose(front_log);
+		free(log_buf);
+	}
 	for (int i = 0; i < nstarted; i++) pthread_join(tids[i], NULL);
 	if (thread_failed && rc == EMUB_OK) rc = EMUB_ENOMEM;
 

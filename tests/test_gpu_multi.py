@@ -175,3 +175,69 @@ def test_components_shard_over_two_gpus(ctx):
     th2, best2, st = engine.estimate_thetas_multi_devices([0, 1], X, Z, 1, 0, max_tries=6, nchains=6, seed=3, max_slots=32)
     assert st["rc"] == 0
     assert np.array_equal(th1, th2) and np.array_equal(best1, best2)
+
+
+@pytest.mark.gpu
+def test_uploads_are_ordered_before_the_kernels_that_read_them():
+    """Regression: the training vector used to go up with a plain cudaMemcpy (pageable source, <= 64 KB: staged, the DMA
+    runs on the legacy default stream) while k_build_yh read it on a non-blocking stream -- now and then a model
+    trained on whatever the recycled device buffer held, i.e. the PREVIOUS model's training vector.  Models are created
+    on recycled memory with alternating data and evaluated at once; every one must see its own data."""
+    from madaiemulator_b200 import engine
+    n, d = 300, 3
+    X = ds.synthetic_design(n, d)
+    ys = [ds.synthetic_response(X, t) for t in range(3)]
+    th = ds.default_theta_less_amp(d)
+    ctx = engine.Context(0)
+    expect = []
+    for y in ys:
+        m = engine.Model(ctx, X, y, 1, 0, max_slots=2)
+        expect.append(m.loglik_grad_batch(th[None, :])["negL"][0])
+        m.close()
+    assert len(set(expect)) == 3
+    for i in range(60):
+        k = (i * 7) % 3
+        m = engine.Model(ctx, X, ys[(k + 1) % 3], 1, 0, max_slots=2)
+        if i % 2:
+            m.set_training_multi(np.stack([ys[k], ys[(k + 2) % 3]], axis=1))
+            got = m.loglik_grad_batch(np.stack([th, th]), want_grad=False, comp=[0, 1])["negL"]
+            assert got[0] == expect[k] and got[1] == expect[(k + 2) % 3], i
+        else:
+            m.set_training(ys[k])
+            assert m.loglik_grad_batch(th[None, :], want_grad=False)["negL"][0] == expect[k], i
+        m.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_component_sharding_does_not_change_a_bit():
+    """What bench.py's strong-scaling section asserts at N > 1 (`sharded_identical`), on one device: all PCA components
+    in one evaluation front against one component at a time with first_component / component_stride (what every rank
+    does when the components are shared out) -- same thetas, same likelihoods, bit for bit."""
+    from madaiemulator_b200 import engine
+    n, d, ncomp, restarts = 700, 5, 4, 4
+    X, Y = ds.synthetic_model(n, d, nt=ncomp + 1)
+    Z = np.ascontiguousarray(ds.pca_decompose(Y, vfrac=2.0)["Z"][:, :ncomp])
+    ranges = engine.optimization_ranges(engine.POWEREXP, X)
+    ctx = engine.Context(0)
+
+    def train(components, first, stride):
+        m = engine.Model(ctx, X, Z[:, components[0]], engine.POWEREXP, 0, max_slots=restarts * len(components))
+        m.set_training_multi(Z[:, components])
+        th, best, st = engine.estimate_thetas_multi(m, len(components), ranges, max_tries=restarts, nchains=restarts, seed=3,
+                                                    step_max=6, first_component=first, component_stride=stride)
+        m.close()
+        return th, best, st
+
+    th_all, best_all, st_all = train(list(range(ncomp)), 0, 1)
+    assert st_all["value_evaluations"] > 0
+    for rep in range(2):
+        for c in range(ncomp):
+            th, best, _ = train([c], c, ncomp)
+            assert np.array_equal(th[0], th_all[c]) and best[0] == best_all[c], (rep, c)
+    # two components per "rank"
+    for r in range(2):
+        comps = [r, r + 2]
+        th, best, _ = train(comps, r, 2)
+        assert np.array_equal(th, th_all[comps]) and np.array_equal(best, best_all[comps])
+    ctx.close()
