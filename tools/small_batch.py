@@ -16,10 +16,16 @@ for B in (1, 2, 4, 8):
     for _ in range(10):
         m.loglik_grad_batch(th)
     ms = (time.time() - t0) * 100.0
+    for _ in range(3):
+        m.loglik_grad_batch(th, want_grad=False)
+    t0 = time.time()
+    for _ in range(10):
+        m.loglik_grad_batch(th, want_grad=False)
+    ms_val = (time.time() - t0) * 100.0
     ctx.profile(True)
     m.loglik_grad_batch(th)
     prof = ctx.profile_read()
     ctx.profile(False)
-    print("B=%d: %.3f ms per call (%.1f evals/s); profile-mode split:" % (B, ms, B / ms * 1e3),
+    print("B=%d: %.3f ms per call (%.1f evals/s), value only %.3f ms (%.1f evals/s); profile-mode split:" % (B, ms, B / ms * 1e3, ms_val, B / ms_val * 1e3),
           ", ".join("%s %.3f ms/%d" % (k, v["ms"], v["launches"]) for k, v in prof.items() if v["launches"]))
     m.close()
