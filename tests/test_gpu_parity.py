@@ -395,6 +395,8 @@ def test_cfg4_n8192_d15_properties(ctx):
     r1 = m.loglik_grad_batch(th[None, :])
     assert r1["negL"][0] == r["negL"][0]
     W = np.tril(m.debug_fetch(0, 1))
+    Cinv = np.tril(m.debug_fetch(0, 0))  # before cov_matrix below, which builds its matrix in the same scratch buffer
+    Cinv = Cinv + np.tril(Cinv, -1).T
     rows = np.array([0, 127, 128, 4095, 4096, 8000, 8191])
     E = np.zeros((len(rows), n))
     E[np.arange(len(rows)), rows] = 1.0
@@ -413,8 +415,6 @@ def test_cfg4_n8192_d15_properties(ctx):
     assert relerr(r["sigma2"][0], (u @ z) / n) < 1e-8
     # finite-difference consistency of the nugget component is NOT expected (Q9: the reference's "gradient" is not
     # the gradient of its objective); instead check the fused formula against numpy on the explicit inverse
-    Cinv = np.tril(m.debug_fetch(0, 0))
-    Cinv = Cinv + np.tril(Cinv, -1).T
     alpha = Cinv @ y
     nug = np.exp(th[0])
     g0 = -1.0 * (-0.5 * nug * np.trace(Cinv) + 0.5 * nug * (alpha @ alpha))
