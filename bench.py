@@ -258,6 +258,8 @@ def strong_section(engine, ds, ctx, rank, world, local, barrier, max_over_ranks)
     dev = torch.device("cuda", local)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
+    last_per_rank = []  # device seconds of every rank in the last collective timed() region
+
     def timed(fn, collective=True):
         """seconds between two events on the library's stream around fn(); collective: barrier + synchronize on both
         sides and the max over ranks (the sharded runs); otherwise this rank alone (the single-device repeat)"""
@@ -275,7 +277,14 @@ def strong_section(engine, ds, ctx, rank, world, local, barrier, max_over_ranks)
         dt = e0.elapsed_time(e1) * 1e-3
         if collective:
             barrier()
-            return r, max_over_ranks(dt), max_over_ranks(wall)
+            per_rank = [dt]
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                outs = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(outs, t)
+                per_rank = [float(o.item()) for o in outs]
+            last_per_rank[:] = per_rank
+            return r, max(per_rank), max_over_ranks(wall)
         return r, dt, wall
 
     def gather_rows(local_rows, counts):
@@ -297,7 +306,8 @@ def strong_section(engine, ds, ctx, rank, world, local, barrier, max_over_ranks)
     counts = [b - a for a, b in (sharding.block_range(CFG5_POINTS, world, r) for r in range(world))]
     cfg5 = {"workload": "cfg5: %d query points on a trained-model shape n=%d, d=%d, host buffers in and out "
                         "(emub_predict_batch); contiguous block per rank, final all_gather of (mean, variance)" % (CFG5_POINTS, N_MODEL, D_MODEL),
-            "seconds": t_sh, "wall_seconds": wall_sh, "points_per_s": CFG5_POINTS / t_sh, "points_per_rank": counts}
+            "seconds": t_sh, "wall_seconds": wall_sh, "points_per_s": CFG5_POINTS / t_sh, "points_per_rank": counts,
+            "seconds_per_rank": [round(x, 4) for x in last_per_rank]}
     if world > 1:
         blocks = gather_rows(np.column_stack([mean, var]), counts)
         if rank == 0:
@@ -334,6 +344,7 @@ def strong_section(engine, ds, ctx, rank, world, local, barrier, max_over_ranks)
 
     mine = sharding.round_robin(CFG4_COMPONENTS, world, rank)
     (th_loc, best_loc, st), t_sh, wall_sh, slots = train(mine, rank, world, True)
+    cfg4_per_rank = [round(x, 4) for x in last_per_rank]
     counts = [len(sharding.round_robin(CFG4_COMPONENTS, world, r)) for r in range(world)]
     blocks = gather_rows(np.column_stack([th_loc, best_loc]), counts)
     gathered = sharding.scatter_round_robin(blocks, CFG4_COMPONENTS)
@@ -345,7 +356,8 @@ def strong_section(engine, ds, ctx, rank, world, local, barrier, max_over_ranks)
     cfg4 = {"workload": "cfg4: %d PCA components, n=%d, d=%d, power-exponential, %d restarts per component, <= %d BFGS "
                         "iterations each (emub_estimate_thetas_multi); component c -> rank c mod N, final all_gather of thetas"
                         % (CFG4_COMPONENTS, CFG4_N, CFG4_D, CFG4_RESTARTS, CFG4_STEP_MAX),
-            "seconds": t_sh, "wall_seconds": wall_sh, "evaluations": int(evals[0]), "value_only_evaluations": int(evals[2]),
+            "seconds": t_sh, "wall_seconds": wall_sh, "seconds_per_rank": cfg4_per_rank, "evaluations": int(evals[0]),
+            "value_only_evaluations": int(evals[2]),
             "batched_calls": int(evals[1]), "evals_per_s": evals[0] / t_sh, "components_per_rank": counts,
             "front_width_per_rank": CFG4_RESTARTS * len(mine), "slots_rank0": slots,
             "finite_components": int(np.sum(gathered[:, nth] > -1e6)),
