@@ -12,6 +12,7 @@
  *   emulateAtPointList, emulateAtPoint                               src/libEmu/emulate-fns.c:73,138
  *   makeCovMatrix[_fnptr], makeKVector[_fnptr]                       src/libEmu/emulator.c:607,636,553,578
  *   emulateQuick, chol_inverse_cov_matrix                            src/libEmu/emulate-fns.c:201,275
+ *   emulate_model_results, emulate_ith_location                      src/libEmu/emulate-fns.c:13,234
  *
  * Engine handles are kept in side tables keyed by the reference's struct pointers, so no reference
  * struct changes.  Environment: EMUB_DEVICE (default 0), EMUB_SLOTS (in-flight evaluations per model,
@@ -28,6 +29,7 @@
 #include "modelstruct.h"
 #include "optstruct.h"
 #include "emulator_struct.h"
+#include "resultstruct.h"
 #include "libEmu/emulator.h"
 #include "libEmu/maxmultimin.h"
 #include "libEmu/estimate_threaded.h"
@@ -459,6 +461,52 @@ void emulateQuick(modelstruct *the_model, gsl_vector *the_point, optstruct *opti
 {
 	(void)h_matrix; (void)cinverse; (void)beta_vector;
 	emulateAtPoint(the_model, the_point, options, mean_out, var_out);
+}
+
+/* emulate-fns.c:13 -- the reference builds C, C^-1 and beta on the host and walks emulate_ith_location over the rows of
+ * results->new_x; here: one emulator, one batched prediction.  Its two debugging prints are kept (regression
+ * coefficients to stderr, the first coordinate of every point to stdout, :39-50). */
+void emulate_model_results(modelstruct *the_model, optstruct *options, resultstruct *results)
+{
+	const int mq = options->nemulate_points;
+	double th[GLUE_TH], beta[GLUE_TH];
+	for (int i = 0; i < options->nthetas; i++) th[i] = gsl_vector_get(the_model->thetas, i);
+	double *mean = (double *)malloc(sizeof(double) * (size_t)(mq > 0 ? mq : 1));
+	double *var = (double *)malloc(sizeof(double) * (size_t)(mq > 0 ? mq : 1));
+	emub_emulator *eh = NULL;
+	pthread_mutex_lock(&g_call_mu);
+	emub_model *m = glue_model_for_opts(the_model, options);
+	if (emub_emulator_create(m, th, &eh) != EMUB_OK) { /* chol_inverse_cov_matrix exits on a failed factorisation, :282-285 */
+		fprintf(stderr, "emulate_model_results: %s\n", emub_last_error());
+		exit(EXIT_FAILURE);
+	}
+	emub_emulator_beta(eh, beta);
+	const int rc = emub_predict_batch(eh, results->new_x->data, (int)results->new_x->tda, mq, mean, var);
+	emub_emulator_destroy(eh);
+	pthread_mutex_unlock(&g_call_mu);
+	if (rc != EMUB_OK) glue_die("emub_predict_batch");
+	fprintf(stderr, "regression cpts: ");
+	for (int i = 0; i < options->nregression_fns; i++) fprintf(stderr, "%g ", beta[i]);
+	fprintf(stderr, "\n");
+	for (int i = 0; i < mq; i++) printf("%g\n", gsl_matrix_get(results->new_x, i, 0));
+	for (int i = 0; i < mq; i++) {
+		gsl_vector_set(results->emulated_mean, i, mean[i]);
+		gsl_vector_set(results->emulated_var, i, var[i]);
+	}
+	free(mean); free(var);
+}
+
+/* emulate-fns.c:234 -- one row of results->new_x against precomputed host-side set-up data: like emulateQuick, the
+ * engine's cached factor of (the_model, the_model->thetas) stands in for h_matrix / cinverse / beta_vector */
+void emulate_ith_location(modelstruct *the_model, optstruct *options, resultstruct *results, int i, gsl_matrix *h_matrix,
+                          gsl_matrix *cinverse, gsl_vector *beta_vector)
+{
+	(void)h_matrix; (void)cinverse; (void)beta_vector;
+	gsl_vector_view row = gsl_matrix_row(results->new_x, (size_t)i);
+	double mean = 0.0, var = 0.0;
+	emulateAtPoint(the_model, &row.vector, options, &mean, &var);
+	gsl_vector_set(results->emulated_mean, i, mean);
+	gsl_vector_set(results->emulated_var, i, var);
 }
 
 /* emulator.c:636 -- the kernel is identified by the function pointer the caller passes */

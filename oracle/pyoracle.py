@@ -211,6 +211,9 @@ class RefOracle:
             if hasattr(L, "ref_emulate_at_point_list"):
                 L.ref_emulate_at_point_list.argtypes = [_vp, _dp, _dp, _ci, _ci, _dp, _dp]
                 L.ref_emulate_at_point_list.restype = None
+            if hasattr(L, "ref_emulate_model_results"):
+                L.ref_emulate_model_results.argtypes = [_vp, _dp, _dp, _ci, _dp, _dp]
+                L.ref_emulate_model_results.restype = None
             L.ref_emulator_beta.argtypes = [_vp, _dp]
             L.ref_max_with_multimin.restype = ctypes.c_double
             L.ref_max_with_multimin.argtypes = [_vp, _ci, ctypes.c_ulong, _dp]
@@ -314,6 +317,14 @@ class RefOracle:
         m = pts.shape[0]
         mean, var = np.empty(m), np.empty(m)
         self.L.ref_emulate_at_point_list(self.h, _P(_c(thetas)), _P(pts), m, 1 if single else 0, _P(mean), _P(var))
+        return mean, var
+
+    def emulate_model_results(self, thetas, pts):
+        """emulate_model_results (emulate-fns.c:13) over the rows of pts"""
+        pts = _c(pts).reshape(-1, self.d)
+        m = pts.shape[0]
+        mean, var = np.empty(m), np.empty(m)
+        self.L.ref_emulate_model_results(self.h, _P(_c(thetas)), _P(pts), m, _P(mean), _P(var))
         return mean, var
 
     def max_with_multimin(self, max_tries, seed):

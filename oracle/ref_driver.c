@@ -22,6 +22,7 @@
 #include "modelstruct.h"
 #include "optstruct.h"
 #include "emulator_struct.h"
+#include "resultstruct.h"
 #include "multi_modelstruct.h"
 #include "multivar_support.h"
 #include "libEmu/emulator.h"
@@ -341,6 +342,25 @@ void ref_emulate_at_point_list(void *h, const double *thetas, const double *pts,
 		o->nemulate_points = saved;
 	}
 	restore_stdout(so);
+}
+
+/* -> emulate_model_results, src/libEmu/emulate-fns.c:13: (mean, variance) at the rows of results->new_x (the model's
+ * global covariance / regression function pointers are the ones alloc_modelstruct_2 set) */
+void ref_emulate_model_results(void *h, const double *thetas, const double *pts, int m, double *mean, double *var)
+{
+	ref_model *r = (ref_model *)h;
+	optstruct *o = r->model->options;
+	for (int i = 0; i < o->nthetas; i++) gsl_vector_set(r->model->thetas, i, thetas[i]);
+	const int saved = o->nemulate_points;
+	o->nemulate_points = m;
+	resultstruct res;
+	gsl_matrix_view nx = gsl_matrix_view_array((double *)pts, m, o->nparams);
+	gsl_vector_view mv = gsl_vector_view_array(mean, m), vv = gsl_vector_view_array(var, m);
+	res.new_x = &nx.matrix; res.emulated_mean = &mv.vector; res.emulated_var = &vv.vector; res.options = o; res.model = r->model;
+	int so = silence_stdout(); /* it prints the first coordinate of every point */
+	emulate_model_results(r->model, o, &res);
+	restore_stdout(so);
+	o->nemulate_points = saved;
 }
 
 void ref_emulator_beta(void *e, double *beta_out)

@@ -68,7 +68,8 @@ def test_glue_libraries_define_the_reference_symbols():
 
     hot = ["evalFnMulti", "gradFnMulti", "evalFnGradMulti", "estimateSigmaFull", "estimate_thetas_threaded", "alloc_emulator_struct",
            "free_emulator_struct", "emulate_point", "makeCovMatrix_fnptr", "emulateAtPointList", "emulateAtPoint",
-           "makeCovMatrix", "makeKVector_fnptr", "makeKVector", "emulateQuick", "chol_inverse_cov_matrix"]
+           "makeCovMatrix", "makeKVector_fnptr", "makeKVector", "emulateQuick", "chol_inverse_cov_matrix",
+           "emulate_model_results", "emulate_ith_location"]
     mv = ["estimate_multi", "alloc_multi_emulator", "free_multi_emulator", "emulate_point_multi", "emulate_point_multi_pca"]
     b, m = defined(base), defined(multi)
     for name in hot:

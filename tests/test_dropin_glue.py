@@ -59,6 +59,11 @@ def test_point_list_entry_points_run_on_the_engine(oracles, name):
     m2, v2 = dro.emulate_at_point_list(c["theta_full"], pts)
     assert relerr(m2, m1, 1e-3) < 1e-9
     assert np.max(np.abs(v2 - v1)) < 1e-9 * max(1.0, float(c["kappa"]))
+    # emulate_model_results (emulate-fns.c:13): the same list through the resultstruct front door
+    m4, v4 = ref.emulate_model_results(c["theta_full"], pts)
+    m5, v5 = dro.emulate_model_results(c["theta_full"], pts)
+    assert relerr(m4, m1, 1e-3) < 1e-12 and relerr(m5, m4, 1e-3) < 1e-9
+    assert np.max(np.abs(v5 - v4)) < 1e-9 * max(1.0, float(c["kappa"]))
     m3, v3 = dro.emulate_at_point_list(c["theta_full"], pts[:5], single=True)
     # single points take the latency path (emub_predict_few): the same sums in another order
     assert relerr(m3, m2[:5], 1e-3) < 1e-11 and np.max(np.abs(v3 - v2[:5])) < 1e-11 * max(1.0, float(c["kappa"]))
