@@ -12,6 +12,13 @@
  *
  * There is NO CPU fallback: every call runs CUDA kernels on the context's device and returns
  * EMUB_ECUDA when that is impossible.
+ *
+ * Limits: nparams <= 64, 1 + nregression_fns <= 104 (regression_order * nparams <= 102), at most 1024
+ * observables / components in emub_predict_multi; anything larger is refused with EMUB_EINVAL.
+ * Environment (all optional): EMUB_NO_GRAPHS=1 (direct launches instead of CUDA-graph replay),
+ * EMUB_SMALL_CTAS (products with at most this many 64 x 64 sub-tiles use 32 x 32 ones, default 296),
+ * EMUB_AUX_MAX (use the factorisation's side streams when a stream group holds at most this many
+ * matrices, default 8, 0 = never).
  */
 #ifndef EMU_B200_H
 #define EMU_B200_H

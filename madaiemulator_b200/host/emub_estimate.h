@@ -10,6 +10,8 @@
  * (include/emu_b200.h).  Results do not depend on thread timing: start points come from a counter-based
  * generator keyed by (seed, try index) and the batched evaluator is bit-wise independent of the batch
  * composition.
+ * Debugging aid: EMUB_FRONT_LOG=<file> appends every batched call of a front as text (B, then per point: component,
+ * gradient flag, theta | -L, sigma^2, status), kept in memory and written when the front ends.
  */
 #ifndef EMUB_ESTIMATE_H
 #define EMUB_ESTIMATE_H
