@@ -236,6 +236,7 @@ static int glue_eval(const gsl_vector *theta_vec, void *params_in, int want_grad
 	struct estimate_thetas_params *p = (struct estimate_thetas_params *)params_in;
 	double th[GLUE_TH];
 	int status = 0;
+	if (theta_vec->size > GLUE_TH) { fprintf(stderr, "libemu_glue: %zu thetas: more than the engine takes\n", theta_vec->size); exit(EXIT_FAILURE); }
 	for (size_t i = 0; i < theta_vec->size; i++) th[i] = gsl_vector_get(theta_vec, i);
 	pthread_mutex_lock(&g_call_mu);
 	emub_model *m = glue_model_for_opts(p->the_model, p->options);

@@ -165,7 +165,8 @@ void setupEmulateMCMulti(double *xmodel_in, int *nparams_in, double *training_in
 	if (!ctx || emub_model_create(ctx, X, d, n, d, Y, *cov_fn_index_in, *regression_order_in, 1, &mcm_model) != EMUB_OK ||
 	    emub_model_set_training_multi(mcm_model, Y, ny, ny) != EMUB_OK)
 		mc_die("setupEmulateMCMulti");
-	mcm_emus = (emub_emulator **)calloc((size_t)ny, sizeof(emub_emulator *));
+	mcm_emus = (emub_emulator **)calloc((size_t)(ny > 0 ? ny : 1), sizeof(emub_emulator *));
+	if (!mcm_emus) { fprintf(stderr, "setupEmulateMCMulti: out of memory\n"); exit(EXIT_FAILURE); }
 	mcm_n = ny; mcm_d = d;
 	for (int i = 0; i < ny; i++)
 		if (emub_emulator_create_comp(mcm_model, i, TH + (size_t)i * nth, &mcm_emus[i]) != EMUB_OK) mc_die("setupEmulateMCMulti");
