@@ -49,7 +49,7 @@ const char *emub_version(void);
 /* The cudaStream_t (as void*) that group-0 kernels are launched on, so a caller can record its own
  * CUDA events around library calls. */
 void *emub_ctx_stream(emub_ctx *ctx);
-/* number of concurrently scheduled matrix groups (streams); 1..4, default 2 */
+/* number of concurrently scheduled matrix groups (streams); 1..4, default 4 */
 int emub_ctx_set_groups(emub_ctx *ctx, int ngroups);
 /* the launch sequence of a batch chunk (~160 dependent kernels per group) is captured once into a CUDA graph and
  * replayed; on by default (EMUB_NO_GRAPHS=1 or on = 0 issues the kernels one by one) */

@@ -200,7 +200,7 @@ extern "C" int emub_ctx_create(int device, emub_ctx **out)
 	emub_ctx *c = new emub_ctx();
 	memset(c, 0, sizeof(*c));
 	c->device = device;
-	c->ngroups = 2;
+	c->ngroups = 4; // measured best from B = 4 upwards (profiles/r02_groups_sweep.txt); a call uses min(ngroups, points)
 	c->use_graphs = getenv("EMUB_NO_GRAPHS") ? 0 : 1;
 	// half of what the default configuration keeps resident (148 SMs x 4 CTAs)
 	c->small_launch_ctas = getenv("EMUB_SMALL_CTAS") ? atoll(getenv("EMUB_SMALL_CTAS")) : 296;
